@@ -1,0 +1,196 @@
+/*
+ * tfem_b200.h -- C ABI of the B200-native element-assembly hot path of torch_fem.
+ *
+ * The reference (Nicolas-Zamorano/pytorch_fem_solver, package `torch_fem`) is pure
+ * Python/PyTorch and has no FFI of its own; the boundary is its Python object API
+ * (SURVEY.md section 8(b)).  Every entry point below replaces the tensor program of
+ * the reference method it cites (paths relative to the reference's `torch_fem/`).
+ * The Python package binds these symbols with ctypes and registers them as
+ * `torch.library` custom ops (pytorch_fem_solver_b200/ops.py); INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: device pointers, sizes, scalars; no torch / C++ types.
+ *   - every `T*` is a DEVICE pointer unless the name says `host`; T is double for the
+ *     `_f64` symbols and float for `_f32` (same argument lists; declared by macro).
+ *   - indices are int32_t; element/vertex counts are int64_t.
+ *   - the last argument is a `cudaStream_t` passed as `void*`; calls only enqueue work:
+ *     they never allocate, free, synchronise or throw, and are re-entrant.
+ *   - return value: TFEM_OK (0) or a negative tfem_status.
+ *   - batched meshes (MeshesTri / Patches / FracturesTri) are passed flattened:
+ *     element e belongs to mesh  m = e / n_el_per_mesh  and its geometry vertex ids are
+ *     conn[e][k] + m * n_vert_per_mesh.  A single mesh has n_el_per_mesh == n_el.
+ *   - fracture maps are optional (NULL for planar meshes): frac_jac [n_mesh,3,2],
+ *     frac_inv [n_mesh,2,3], frac_det [n_mesh], frac_t [n_mesh,3].  With maps the
+ *     spatial dimension d of points / gradients is 3, otherwise 2.
+ *   - any OUTPUT pointer may be NULL, in which case that output is skipped.
+ */
+#ifndef TFEM_B200_H
+#define TFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tfem_status {
+  TFEM_OK = 0,
+  TFEM_ERR_BAD_ARG = -1,      /* NULL required pointer, negative size, unknown enum */
+  TFEM_ERR_UNSUPPORTED = -2,  /* e.g. quadrature order outside the reference's tables */
+  TFEM_ERR_LAUNCH = -3,       /* cudaGetLastError() != cudaSuccess after enqueue */
+  TFEM_ERR_TOO_LARGE = -4     /* a count does not fit the 32-bit index type */
+} tfem_status;
+
+/* Source term f evaluated inside the kernels at the mapped quadrature points.
+ * Covers the load used by every reference test/example
+ * (tests/test_assembly.py:75-84, examples/example_weak.py:59-75). */
+typedef enum tfem_source_kind {
+  TFEM_SRC_NONE = 0,     /* f == 0 */
+  TFEM_SRC_SAMPLED = 1,  /* f given at the quadrature points: f_q[n_el, n_q]       */
+  TFEM_SRC_CONST = 2,    /* f == p[0]                                               */
+  TFEM_SRC_SINSIN = 3    /* f == p[0] * sin(p[1]*x) * sin(p[2]*y)                   */
+} tfem_source_kind;
+
+typedef struct tfem_source {
+  int32_t kind;
+  double p[4];
+} tfem_source;
+
+/* Which bilinear form the fused kernels integrate: alpha * grad u . grad v + beta * u v
+ * (examples/example_weak.py:78-81, tests/test_assembly.py:68-73). */
+typedef struct tfem_bilinear {
+  double alpha; /* stiffness coefficient */
+  double beta;  /* mass coefficient      */
+} tfem_bilinear;
+
+/* Tile plan of the fused assembly kernel (all pointers DEVICE memory, built once per mesh by
+ * pytorch_fem_solver_b200/csr.py; layouts documented in DESIGN.md "tile plan").
+ * A tile owns a set of CSR rows; its elements are all elements touching those rows. */
+typedef struct tfem_tile_plan {
+  int64_t n_tiles;
+  const int32_t* tile_ptr;        /* [n_tiles+1,4] first vertex / element / row / run of each tile  */
+  const int32_t* tile_vert;       /* geometry vertex id (row of `coords`) of each tile-local vertex  */
+  const uint32_t* tile_elem;      /* tile-local connectivity, v0 | v1<<10 | v2<<20                    */
+  const int32_t* row_id;          /* global row (DOF) of each tile row                                 */
+  const int32_t* row_meta;        /* out_base | pos_diag<<16 : first slot of the row in the tile output*/
+  const int32_t* row_corner_ptr;  /* [n_rows+1] offsets into `corner`                                 */
+  const uint32_t* corner;         /* elem | k<<12 | posA<<16 | posB<<24 per (row, incident element)  */
+  const int32_t* run_start;       /* CSR offset of the first entry of each run of consecutive rows    */
+  const int32_t* run_meta;        /* out_base | len<<16 of each run                                    */
+  int32_t max_vert, max_elem, max_out, max_rows; /* per-tile maxima (shared-memory sizing)           */
+} tfem_tile_plan;
+
+int tfem_abi_version(void);
+const char* tfem_status_string(int status);
+/* Bind the calling thread to a device before enqueuing (the library links the static
+ * CUDA runtime; the Python wrapper calls this with the tensors' device index). */
+int tfem_set_device(int device);
+/* Number of SMs of the current device (grid sizing of persistent kernels; 148 on B200). */
+int tfem_sm_count(void);
+
+#define TFEM_DECLARE(T, SUF)                                                                        \
+  /* a1-a9: AbstractBasis._compute_integral_values (basis/abstract_basis.py:42-63) with          \
+   * Basis._compute_jacobian_map/_integration_points/_integral_weights (basis/basis.py:87-96),   \
+   * ElementTri.compute_det_and_inv_map/shape functions (element/element_tri.py:28-41,132-145), \
+   * the gather of mesh/abstract_mesh.py:257-262 / mesh/meshes_tri.py:33-41, and the fracture   \
+   * post-scaling of basis/fracture_basis.py:20-26,189-207.                                     \
+   * inv_jac [n_el,2,d], v_grad [n_el,3,d], x_q [n_el,n_q,d], dx [n_el,n_q]. */                 \
+  int tfem_tri_p1_geometry_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh,     \
+                                 const T* coords, const int32_t* conn, int quad_order,             \
+                                 const T* frac_jac, const T* frac_inv, const T* frac_det,          \
+                                 const T* frac_t, T* inv_jac, T* v_grad, T* x_q, T* dx,            \
+                                 void* stream);                                                    \
+  /* Edge variant: basis/interior_edges_basis.py:63-72, interior_edges_fracture_basis.py:65-86,  \
+   * element/element_line.py:45-73.  edge_coords [n_edge,2,2] (2-D end points).                 \
+   * inv_jac [n_edge], v_grad [n_edge,2], x_q [n_edge,n_q,d], dx [n_edge,n_q]. */               \
+  int tfem_edge_p1_geometry_##SUF(int64_t n_edge, int64_t n_edge_per_mesh, const T* edge_coords,   \
+                                  int quad_order, const T* frac_jac, const T* frac_det,            \
+                                  const T* frac_t, T* inv_jac, T* v_grad, T* x_q, T* dx,           \
+                                  void* stream);                                                   \
+  /* `(f * dx).sum(-3)` of basis/abstract_basis.py:72,83,104 for an arbitrary user integrand:    \
+   * local[e,c] = sum_q dx[e,q] * f[e*stride_e + q*stride_q + c], c < m (strides in elements;    \
+   * a stride of 0 broadcasts, as the reference's broadcasting does). */                         \
+  int tfem_quad_reduce_##SUF(int64_t n_el, int n_q, int m, const T* integrand, int64_t stride_e,    \
+                             int64_t stride_q, const T* dx, T* local, void* stream);                \
+  /* The local-to-global scatter of basis/abstract_basis.py:87-91,106-110, as a deterministic    \
+   * segmented reduction instead of index_put_(accumulate=True):                                 \
+   * out[p] = sum_{s in [seg[p], seg[p+1])} values[perm[s]], summed in increasing s.              \
+   * With (seg, perm) = stable sort of `bilinear_form_idx` this yields the CSR value array,       \
+   * with the sort of `linear_form_idx` the global vector. */                                     \
+  int tfem_scatter_bilinear_##SUF(int64_t nnz, const int32_t* seg, const int32_t* perm,            \
+                                  const T* local, T* csr_val, void* stream);                       \
+  int tfem_scatter_linear_##SUF(int64_t n_dof, const int32_t* seg, const int32_t* perm,            \
+                                const T* local, T* vec, void* stream);                             \
+  /* Fused local forms (never materialising v, v_grad, x_q, dx):                                 \
+   * local_mat[e,i,j] = sum_q dx (alpha grad phi_i . grad phi_j + beta phi_i phi_j)   [n_el,3,3]   \
+   * local_vec[e,i]   = sum_q dx f(x_q) phi_i                                        [n_el,3]     \
+   * Forms: examples/example_weak.py:78-81, tests/test_assembly.py:68-84. */                      \
+  int tfem_tri_p1_local_forms_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh,  \
+                                    const T* coords, const int32_t* conn, int quad_order,          \
+                                    const T* frac_jac, const T* frac_inv, const T* frac_det,       \
+                                    const T* frac_t, const tfem_bilinear* host_form,               \
+                                    const tfem_source* host_source,                                \
+                                    const T* f_q, T* local_mat, T* local_vec, void* stream);       \
+  /* Fused assembly to CSR + load vector in ONE pass over row tiles (BASELINE config 2):          \
+   * csr_val[p] = sum over elements of alpha K_loc + beta M_loc, load[r] = sum of local loads,    \
+   * each summed in increasing element order (deterministic, no atomics).  The tile plan is      \
+   * built once from the connectivity by pytorch_fem_solver_b200/csr.py. */                      \
+  int tfem_tri_p1_assemble_csr_##SUF(const tfem_tile_plan* host_plan, const T* coords,             \
+                                     int quad_order, const tfem_bilinear* host_form,               \
+                                     const tfem_source* host_source, T* csr_val, T* load,          \
+                                     void* stream);                                                \
+  /* Weak residual r_i = sum_q dx (f phi_i - grad phi_i . grad u) of                              \
+   * examples/example_weak.py:64-75 / example_patches.py:102-113 /                               \
+   * example_fracture_vpinns.py:104-113 integrated by basis/abstract_basis.py:95-112:            \
+   * per-element part local_vec [n_el,3]; grad_u [n_el,n_q,d]. */                                 \
+  int tfem_weak_residual_local_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh, \
+                                     const T* coords, const int32_t* conn, int quad_order,         \
+                                     const T* frac_jac, const T* frac_inv, const T* frac_det,      \
+                                     const T* frac_t, const tfem_source* host_source,              \
+                                     const T* f_q, const T* grad_u, T* local_vec, void* stream);   \
+  /* Adjoint of the above w.r.t. grad_u (what autograd derives from index_put_/sum/matmul):       \
+   * grad_u_bar[e,q,:] = -dx[e,q] * sum_i grad phi_i[e,:] * r_bar[dof_conn[e,i]]. */              \
+  int tfem_weak_residual_bwd_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh,   \
+                                   const T* coords, const int32_t* conn, const int32_t* dof_conn,  \
+                                   int quad_order, const T* frac_jac, const T* frac_inv,           \
+                                   const T* frac_det, const T* r_bar, T* grad_u_bar,               \
+                                   void* stream);                                                  \
+  /* Basis.interpolate(self, u) (basis/basis.py:105-112,149-159; fracture_basis.py:214-223):     \
+   * val[e,q] = sum_i u[dof_conn[e,i]] phi_i(q),  grad[e,:] = sum_i u[...] grad phi_i[e,:]. */    \
+  int tfem_interp_cells_##SUF(int64_t n_el, const int32_t* dof_conn, const T* v_grad, int d,       \
+                              int quad_order, const T* u, T* val, T* grad, void* stream);          \
+  /* Basis.interpolate(InteriorEdgesBasis, u) (basis/basis.py:114-159;                            \
+   * fracture_basis.py:225-257; element/abstract_element.py:18-26): both cells of every          \
+   * interior edge evaluated at the edge quadrature points.  edge_cells [n_edge,2] are cell ids   \
+   * local to the mesh of the edge, conn [n_el,3] the ids used to index `u`,                      \
+   * first_vertex [n_el,d], inv_jac [n_el,2,d], x_q [n_edge,n_q,d].                              \
+   * val [n_edge,2,n_q], grad [n_edge,2,d]. */                                                    \
+  int tfem_interp_edges_##SUF(int64_t n_edge, int64_t n_edge_per_mesh, int64_t n_el_per_mesh,      \
+                              const int32_t* edge_cells, const int32_t* conn,                      \
+                              const T* first_vertex, const T* inv_jac, int d, const T* x_q,        \
+                              int n_q, const T* u, T* val, T* grad, void* stream);                 \
+  /* Jump estimator eta_E = sum_q dx h_E (grad u+ . n - grad u- . n)^2                            \
+   * (examples/example_jump.py:75-87 integrated by basis/abstract_basis.py:65-72).              \
+   * grad_edges [n_edge,2,d] from tfem_interp_edges, normals [n_edge,d], h_e [n_edge],           \
+   * dx [n_edge,n_q]. */                                                                         \
+  int tfem_edge_jump_##SUF(int64_t n_edge, int d, int n_q, const T* grad_edges, const T* normals,  \
+                           const T* h_e, const T* dx, T* eta, void* stream);                       \
+  /* Multi-GPU interface exchange: gather interface entries into a             \
+   * contiguous send buffer, and add a received buffer into the owner's entries                  \
+   * (idx entries are unique, so no atomics). */                                                 \
+  int tfem_iface_pack_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf, void* stream);    \
+  int tfem_iface_unpack_add_##SUF(int64_t n, const int32_t* idx, const T* buf, T* dst,             \
+                                  void* stream);
+
+TFEM_DECLARE(double, f64)
+TFEM_DECLARE(float, f32)
+
+/* Symbolic phase helper (integer, one-time): COO keys of basis/basis.py:72-75,
+ * key[9e+3i+j] = dof_conn[e][j] * n_dof + dof_conn[e][i]   (row-major (row, col)). */
+int tfem_coo_keys(int64_t n_el, const int32_t* dof_conn, int64_t n_dof, int64_t* keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFEM_B200_H */

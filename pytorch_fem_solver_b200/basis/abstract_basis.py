@@ -1,0 +1,346 @@
+"""The integration engine, re-designed around fused CUDA kernels.
+
+API and tensor shapes follow the reference's `AbstractBasis`
+(torch_fem/basis/abstract_basis.py:10-195).  What differs:
+
+* geometry (`v_grad`, `integration_points`, `_dx`, `_inv_map_jacobian`) comes from ONE kernel
+  (`tfem_tri_p1_geometry`) and is produced lazily -- the fused assembly forms never need it;
+* `integrate_*` reduce over quadrature points with `tfem_quad_reduce` and scatter with a
+  deterministic segmented reduction into CSR values (`tfem_scatter_*`), not `index_put_` into a
+  dense `(N_d, N_d)` zero matrix (reference :81-91);
+* named forms from `pytorch_fem_solver_b200.forms` skip the integrand altogether;
+* results are dense tensors of the reference's shapes when they are small, CSR otherwise
+  (`layout=` chooses explicitly).
+"""
+
+from __future__ import annotations
+
+import abc
+from dataclasses import dataclass
+from typing import Any, Callable, Optional, Tuple
+
+import torch
+
+from .. import csr as csr_mod
+from .. import forms, ops
+from ..element.abstract_element import AbstractElement
+from ..mesh.abstract_mesh import AbstractMesh
+
+DENSE_LIMIT = 8192  # largest n_dof returned as a dense (n_dof, n_dof) tensor by default
+
+
+@dataclass
+class CellLayout:
+    """Flattened view of the (possibly batched) triangle mesh the kernels consume."""
+
+    coords: torch.Tensor  # (V_total, 2)
+    conn: torch.Tensor  # (N_total, 3) int32, ids local to each mesh
+    n_el_per_mesh: int
+    n_vert_per_mesh: int
+    lead: Tuple[int, ...]  # leading shape of per-element results, e.g. (N,), (P,4), (F,N)
+    frac: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]] = None  # jac, inv, det, t
+
+    @property
+    def d(self) -> int:
+        return 3 if self.frac is not None else 2
+
+    @property
+    def n_total(self) -> int:
+        return self.conn.shape[0]
+
+    def frac_args(self):
+        return self.frac if self.frac is not None else (None, None, None, None)
+
+
+class AbstractBasis(abc.ABC):
+    """P1 basis on a mesh: geometry, index maps and the integrate_* family."""
+
+    def __init__(self, mesh: AbstractMesh, element: AbstractElement):
+        self._element = element
+        self.mesh = ops.place_mesh(mesh)
+        self._geometry = None
+        self._pattern = None
+        self._scatter_inverse = {}
+        self._tile_plans = {}
+        self._layout = self._compute_layout(self.mesh, element)
+        self.v = self._reference_shape_values(element)
+        (
+            self._coords4global_dofs,
+            self._global_dofs4elements,
+            self._nodes4boundary_dofs,
+            self._coords4elements,
+        ) = self._compute_dofs(self.mesh, element)
+        self._basis_parameters = self._compute_basis_parameters(
+            self._coords4global_dofs, self._global_dofs4elements, self._nodes4boundary_dofs
+        )
+
+    # ------------------------------------------------------------------ geometry (lazy)
+    def _reference_shape_values(self, element):
+        nodes = element.gaussian_nodes.to(device=self._layout.coords.device, dtype=self._layout.coords.dtype)
+        return element.compute_barycentric_coordinates(nodes)
+
+    def _compute_integral_values(self):
+        """One kernel for v_grad / points / dx / J^-1 (reference :42-63 as a tensor program)."""
+        lay = self._layout
+        inv_jac, v_grad, x_q, dx = ops.tri_geometry(
+            lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh, self._element.integration_order, *lay.frac_args()
+        )
+        q, d = x_q.shape[1], lay.d
+        self._geometry = {
+            "v_grad": v_grad.reshape(*lay.lead, 1, 3, d),
+            "integration_points": x_q.reshape(*lay.lead, q, 1, d),
+            "_dx": dx.reshape(*lay.lead, q, 1, 1),
+            "_inv_map_jacobian": inv_jac.reshape(*lay.lead, 1, 2, d),
+        }
+
+    def _geo(self, name):
+        if self._geometry is None:
+            self._compute_integral_values()
+        return self._geometry[name]
+
+    def _set_geo(self, name, value):
+        if self._geometry is None:
+            self._compute_integral_values()
+        self._geometry[name] = value
+
+    v_grad = property(lambda self: self._geo("v_grad"), lambda self, v: self._set_geo("v_grad", v))
+    integration_points = property(
+        lambda self: self._geo("integration_points"), lambda self, v: self._set_geo("integration_points", v)
+    )
+    _dx = property(lambda self: self._geo("_dx"), lambda self, v: self._set_geo("_dx", v))
+    _inv_map_jacobian = property(
+        lambda self: self._geo("_inv_map_jacobian"), lambda self, v: self._set_geo("_inv_map_jacobian", v)
+    )
+
+    @property
+    def n_q(self) -> int:
+        return self._element.gaussian_nodes.shape[0]
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self._layout.coords.dtype
+
+    @property
+    def device(self) -> torch.device:
+        return self._layout.coords.device
+
+    # ------------------------------------------------------------------ symbolic structures
+    def _dof_conn_flat(self) -> torch.Tensor:
+        """(N_total,3) int32 global DOF of each element vertex (scatter target)."""
+        return self._flat_dofs
+
+    @property
+    def n_dof_flat(self) -> int:
+        return self._n_dof_flat
+
+    @property
+    def pattern(self) -> csr_mod.CsrPattern:
+        """CSR pattern + COO->CSR permutation of `bilinear_form_idx`, built on first use."""
+        if self._pattern is None:
+            self._pattern = csr_mod.build_pattern(self._dof_conn_flat(), self.n_dof_flat)
+        return self._pattern
+
+    def _inverse(self, kind: str) -> torch.Tensor:
+        """Flat COO index -> output entry (adjoint of the scatter), built on first use."""
+        if kind not in self._scatter_inverse:
+            pat = self.pattern
+            seg, perm = (pat.seg, pat.perm) if kind == "bilinear" else (pat.lin_seg, pat.lin_perm)
+            counts = (seg[1:] - seg[:-1]).long()
+            owner = torch.repeat_interleave(torch.arange(seg.shape[0] - 1, device=seg.device), counts)
+            inverse = torch.empty_like(perm)
+            inverse[perm.long()] = owner.to(torch.int32)
+            self._scatter_inverse[kind] = inverse
+        return self._scatter_inverse[kind]
+
+    def tile_plan(self, rows_per_tile: int = 256, ordering: str = "block"):
+        """Row-tile plan of the fused assembly kernel (planar meshes), cached per setting."""
+        key = (rows_per_tile, ordering)
+        if key not in self._tile_plans:
+            lay = self._layout
+            if lay.frac is not None:
+                raise NotImplementedError("the tiled kernel covers planar meshes; fractures use local_forms + scatter")
+            offsets = (torch.arange(lay.n_total, device=lay.conn.device) // lay.n_el_per_mesh) * lay.n_vert_per_mesh
+            geom_conn = lay.conn.long() + offsets[:, None]
+            dof_conn = self._dof_conn_flat()
+            points = torch.zeros((self.n_dof_flat, 2), dtype=lay.coords.dtype, device=lay.coords.device)
+            points[dof_conn.reshape(-1).long()] = lay.coords[geom_conn.reshape(-1)]
+            self._tile_plans[key] = csr_mod.build_tile_plan(geom_conn, dof_conn, self.pattern, points, rows_per_tile, ordering)
+        return self._tile_plans[key]
+
+    # ------------------------------------------------------------------ integrate_*
+    def _reduce_integrand(self, integrand: torch.Tensor) -> torch.Tensor:
+        """`(f * dx).sum(-3)` -> (N_total, a*b) for an integrand broadcastable to (*lead, q, a, b)."""
+        lay = self._layout
+        n_lead = len(lay.lead)
+        t = integrand.to(self.dtype) if integrand.dtype != self.dtype else integrand
+        while t.dim() < n_lead + 3:
+            t = t.unsqueeze(0)
+        a, b = t.shape[-2], t.shape[-1]
+        q_i = t.shape[-3]
+        if q_i not in (1, self.n_q):
+            raise ValueError(f"integrand has {q_i} quadrature points, the basis has {self.n_q}")
+        if all(s == 1 for s in t.shape[:n_lead]):
+            t3 = t.reshape(1, q_i, a * b)
+        else:
+            t3 = t.expand(*lay.lead, q_i, a, b).reshape(lay.n_total, q_i, a * b)
+        return ops.quad_reduce(t3, self._dx.reshape(lay.n_total, self.n_q))
+
+    def integrate_functional(self, function: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
+        """Per-element integral `(f * dx).sum(-3).sum(-2)` -> (*lead, b) (reference :65-72)."""
+        integrand = function(self, *args, **kwargs)
+        a, b = integrand.shape[-2], integrand.shape[-1]
+        local = self._reduce_integrand(integrand).reshape(*self._layout.lead, a, b)
+        return local.sum(-2)
+
+    def integrate_bilinear_form(
+        self, function: Callable[..., torch.Tensor], *args: Any, layout: Optional[str] = None, **kwargs: Any
+    ) -> torch.Tensor:
+        """Global operator of a bilinear form (reference :74-93).
+
+        `layout`: "dense" (reference shape), "csr" (torch sparse CSR), "values" (CSR value
+        array aligned with `basis.pattern`), None = dense up to DENSE_LIMIT DOFs, CSR above."""
+        pat = self.pattern
+        if isinstance(function, forms.FusedBilinear) and not args and not kwargs:
+            values = self._assemble_fused(function, None)[0]
+        else:
+            local = self._reduce_integrand(function(self, *args, **kwargs))  # (N_total, 9)
+            values = ops.scatter(local.reshape(-1), pat.seg, pat.perm, self._inverse("bilinear"))
+        return self._matrix_result(values, layout)
+
+    def integrate_linear_form(self, function: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
+        """Global vector of a linear form (reference :95-112)."""
+        pat = self.pattern
+        lay = self._layout
+        if isinstance(function, forms.WeakResidual) and len(args) == 1 and not kwargs:
+            src = function.source
+            grad = forms.WeakResidual.field(self, args[0])
+            f_q = None
+            if src.kind == ops.SRC_SAMPLED:
+                f_q = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+            vec = ops.weak_residual(
+                grad.to(self.dtype).reshape(lay.n_total, self.n_q, lay.d).contiguous(), lay.coords, lay.conn,
+                self._dof_conn_flat(), pat.lin_seg, pat.lin_perm, lay.n_el_per_mesh, lay.n_vert_per_mesh,
+                self._element.integration_order, src.kind, list(src.params), f_q, *lay.frac_args(),
+            )
+        elif isinstance(function, forms.Load) and not args and not kwargs:
+            vec = self._assemble_fused(None, function.source)[1]
+        else:
+            local = self._reduce_integrand(function(self, *args, **kwargs))  # (N_total, 3)
+            vec = ops.scatter(local.reshape(-1), pat.lin_seg, pat.lin_perm, self._inverse("linear"))
+        return self._vector_result(vec)
+
+    def assemble(self, bilinear: Optional[forms.FusedBilinear], load: Optional[forms.Load], layout: Optional[str] = None,
+                 path: str = "auto"):
+        """Matrix and load vector of named forms in one pass (BASELINE config 2).
+
+        `path`: "tiled" = single fused kernel over row tiles, "two_pass" = local_forms +
+        scatter kernels, "auto" = tiled for planar meshes with an analytic source."""
+        values, vec = self._assemble_fused(bilinear, load.source if load is not None else None, path)
+        return (
+            self._matrix_result(values, layout) if values is not None else None,
+            self._vector_result(vec) if vec is not None else None,
+        )
+
+    def _assemble_fused(self, bilinear, source, path: str = "auto"):
+        lay = self._layout
+        pat = self.pattern
+        order = self._element.integration_order
+        src = forms.as_source(source)
+        want_mat = bilinear is not None
+        want_vec = source is not None
+        alpha, beta = (bilinear.alpha, bilinear.beta) if want_mat else (0.0, 0.0)
+        tiled_ok = lay.frac is None and src.kind != ops.SRC_SAMPLED
+        if path == "tiled" and not tiled_ok:
+            raise NotImplementedError("tiled assembly needs a planar mesh and an analytic source")
+        if path == "tiled" or (path == "auto" and tiled_ok):
+            plan = self.tile_plan()
+            values = torch.empty(pat.nnz, dtype=self.dtype, device=self.device) if want_mat else None
+            vec = torch.empty(pat.n_dof, dtype=self.dtype, device=self.device) if want_vec else None
+            ops.assemble_csr_tiled(plan.c_struct(), lay.coords, order, alpha, beta, src.kind if want_vec else 0,
+                                   src.params, values, vec)
+            return values, vec
+        f_q = None
+        if want_vec and src.kind == ops.SRC_SAMPLED:
+            f_q = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+        local_mat, local_vec = ops.local_forms(
+            lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh, order, alpha, beta, want_mat,
+            src.kind if want_vec else 0, list(src.params), f_q, *lay.frac_args(),
+        )
+        values = ops.scatter(local_mat.reshape(-1), pat.seg, pat.perm, self._inverse("bilinear")) if want_mat else None
+        vec = ops.scatter(local_vec.reshape(-1), pat.lin_seg, pat.lin_perm, self._inverse("linear")) if want_vec else None
+        return values, vec
+
+    def _matrix_result(self, values: torch.Tensor, layout: Optional[str]) -> torch.Tensor:
+        pat = self.pattern
+        if layout is None:
+            layout = "dense" if pat.n_dof <= DENSE_LIMIT else "csr"
+        if layout == "values":
+            return values
+        if layout == "csr":
+            return pat.to_sparse_csr(values)
+        if layout == "dense":
+            return pat.to_dense(values)
+        raise ValueError(f"unknown layout {layout!r}")
+
+    def _vector_result(self, vec: torch.Tensor) -> torch.Tensor:
+        return vec.reshape(-1, 1)
+
+    # ------------------------------------------------------------------ dense helpers (unchanged behaviour)
+    def reduce(self, tensor: torch.Tensor):
+        """Restrict to interior DOFs (reference :114-117)."""
+        idx = self._basis_parameters["inner_dofs"]
+        if tensor.layout == torch.sparse_csr:
+            tensor = tensor.to_dense()
+        return tensor[idx, :][:, idx] if tensor.size(-1) != 1 else tensor[idx]
+
+    def reshape_for_assembly(self, local_matrices: torch.Tensor, form: str) -> torch.Tensor:
+        """Flatten local matrices in COO order (reference :162-171)."""
+        if form == "bilinear":
+            return local_matrices.reshape(-1)
+        if form == "linear":
+            return local_matrices.reshape(-1, 1)
+        raise NotImplementedError(f"Unknown form type: {form}")
+
+    def solution_tensor(self) -> torch.Tensor:
+        """Zero vector of shape (nb_dofs, 1) (reference :173-175)."""
+        return torch.zeros(self._basis_parameters["linear_form_shape"], dtype=self.dtype, device=self.device)
+
+    def solve(self, matrix: torch.Tensor, solution: torch.Tensor, vector: torch.Tensor, only_inner_dofs: bool = True):
+        """Dense direct solve of the (reduced) system -- outside the assembly path (reference :177-195)."""
+        if only_inner_dofs:
+            matrix = self.reduce(matrix)
+            vector = self.reduce(vector)
+        elif matrix.layout == torch.sparse_csr:
+            matrix = matrix.to_dense()
+        solution[self._basis_parameters["inner_dofs"]] += torch.linalg.solve(matrix, vector)
+        return solution
+
+    # ------------------------------------------------------------------ subclass hooks
+    @abc.abstractmethod
+    def _compute_layout(self, mesh, element) -> CellLayout:
+        raise NotImplementedError
+
+    @abc.abstractmethod
+    def _compute_dofs(self, mesh, element):
+        raise NotImplementedError
+
+    @abc.abstractmethod
+    def _compute_basis_parameters(self, coords4global_dofs, global_dofs4elements, nodes4boundary_dofs) -> dict:
+        raise NotImplementedError
+
+
+class LazyParameters(dict):
+    """dict whose expensive entries (the 9N-long COO index maps) are built on first access."""
+
+    def __init__(self, eager: dict, lazy: dict):
+        super().__init__(eager)
+        self._lazy = lazy
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            self[key] = self._lazy[key]()
+            return self[key]
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy

@@ -1,0 +1,491 @@
+"""torch.library custom ops over the C ABI of include/tfem_b200.h.
+
+Each op allocates its outputs with torch (device memory is torch's job), passes raw device
+pointers and the current CUDA stream to the C entry point, and raises on any failure.
+There is no CPU implementation: calling an op with CPU tensors raises `TfemError`.
+
+Differentiable ops (`quad_reduce`, `scatter`, `weak_residual`) register their adjoints, which
+are again C-ABI kernels, so `loss.backward()` of the VPINN examples
+(reference model/model.py:61-67 over examples/example_weak.py:132-152) stays on the CUDA path.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import Bilinear, TfemError, call, check_cuda, make_source, ptr
+
+NS = "tfem_b200"
+
+TRI_NQ = {1: 1, 2: 3, 3: 4, 4: 6}
+LINE_NQ = {2: 2, 3: 3}
+
+
+def _nq_tri(order: int) -> int:
+    if order not in TRI_NQ:
+        raise NotImplementedError("Integration order not implemented")
+    return TRI_NQ[order]
+
+
+def _i32(t: Tensor) -> Tensor:
+    return t if t.dtype == torch.int32 else t.to(torch.int32)
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry (not differentiable: mesh coordinates are data)
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op(f"{NS}::tri_geometry", mutates_args=())
+def tri_geometry(
+    coords: Tensor,
+    conn: Tensor,
+    n_el_per_mesh: int,
+    n_vert_per_mesh: int,
+    quad_order: int,
+    frac_jac: Optional[Tensor] = None,
+    frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+    frac_t: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """coords (V,2), conn (N,3) int32 -> inv_jac (N,2,d), v_grad (N,3,d), x_q (N,q,d), dx (N,q)."""
+    device = check_cuda(coords, conn, frac_jac, frac_inv, frac_det, frac_t)
+    n_q = _nq_tri(quad_order)
+    n_el = conn.shape[0]
+    d = 3 if frac_jac is not None else 2
+    opts = dict(dtype=coords.dtype, device=device)
+    inv_jac = torch.empty((n_el, 2, d), **opts)
+    v_grad = torch.empty((n_el, 3, d), **opts)
+    x_q = torch.empty((n_el, n_q, d), **opts)
+    dx = torch.empty((n_el, n_q), **opts)
+    call(
+        "tfem_tri_p1_geometry", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+        quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(frac_t), ptr(inv_jac), ptr(v_grad), ptr(x_q), ptr(dx),
+    )
+    return inv_jac, v_grad, x_q, dx
+
+
+@tri_geometry.register_fake
+def _(coords, conn, n_el_per_mesh, n_vert_per_mesh, quad_order, frac_jac=None, frac_inv=None, frac_det=None, frac_t=None):
+    n_el, n_q = conn.shape[0], TRI_NQ[quad_order]
+    d = 3 if frac_jac is not None else 2
+    return (coords.new_empty((n_el, 2, d)), coords.new_empty((n_el, 3, d)), coords.new_empty((n_el, n_q, d)), coords.new_empty((n_el, n_q)))
+
+
+@torch.library.custom_op(f"{NS}::edge_geometry", mutates_args=())
+def edge_geometry(
+    edge_coords: Tensor,
+    n_edge_per_mesh: int,
+    quad_order: int,
+    frac_jac: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+    frac_t: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """edge_coords (E,2,2) -> inv_jac (E,), v_grad (E,2), x_q (E,q,d), dx (E,q)."""
+    device = check_cuda(edge_coords, frac_jac, frac_det, frac_t)
+    if quad_order not in LINE_NQ:
+        raise NotImplementedError("Integration order not implemented")
+    n_q = LINE_NQ[quad_order]
+    n_edge = edge_coords.shape[0]
+    d = 3 if frac_jac is not None else 2
+    opts = dict(dtype=edge_coords.dtype, device=device)
+    inv_jac = torch.empty((n_edge,), **opts)
+    v_grad = torch.empty((n_edge, 2), **opts)
+    x_q = torch.empty((n_edge, n_q, d), **opts)
+    dx = torch.empty((n_edge, n_q), **opts)
+    call(
+        "tfem_edge_p1_geometry", edge_coords.dtype, device, n_edge, n_edge_per_mesh, ptr(edge_coords), quad_order,
+        ptr(frac_jac), ptr(frac_det), ptr(frac_t), ptr(inv_jac), ptr(v_grad), ptr(x_q), ptr(dx),
+    )
+    return inv_jac, v_grad, x_q, dx
+
+
+@edge_geometry.register_fake
+def _(edge_coords, n_edge_per_mesh, quad_order, frac_jac=None, frac_det=None, frac_t=None):
+    n_edge, n_q = edge_coords.shape[0], LINE_NQ[quad_order]
+    d = 3 if frac_jac is not None else 2
+    return (edge_coords.new_empty((n_edge,)), edge_coords.new_empty((n_edge, 2)), edge_coords.new_empty((n_edge, n_q, d)), edge_coords.new_empty((n_edge, n_q)))
+
+
+# ------------------------------------------------------------------------------------------------
+# generic path: quadrature sum of a user integrand + deterministic scatter
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op(f"{NS}::quad_reduce", mutates_args=())
+def quad_reduce(integrand: Tensor, dx: Tensor) -> Tensor:
+    """integrand (N,q|1,m) (a q-stride of 0 broadcasts), dx (N,q) -> (N,m): sum_q dx * f."""
+    device = check_cuda(dx)
+    if not integrand.is_cuda:
+        raise TfemError("tfem_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    n_el, n_q = dx.shape
+    m = integrand.shape[-1]
+    if integrand.stride(-1) != 1 and m > 1:
+        integrand = integrand.contiguous()
+    stride_e = integrand.stride(0) if integrand.shape[0] > 1 else 0
+    stride_q = integrand.stride(1) if integrand.shape[1] > 1 else 0
+    if n_el > 1 and integrand.shape[0] == 1:
+        stride_e = 0
+    out = torch.empty((n_el, m), dtype=dx.dtype, device=device)
+    call("tfem_quad_reduce", dx.dtype, device, n_el, n_q, m, ptr(integrand), stride_e, stride_q, ptr(dx), ptr(out))
+    return out
+
+
+@quad_reduce.register_fake
+def _(integrand, dx):
+    return dx.new_empty((dx.shape[0], integrand.shape[-1]))
+
+
+def _quad_reduce_setup(ctx, inputs, output):
+    integrand, dx = inputs
+    ctx.save_for_backward(dx)
+    ctx.shape = integrand.shape
+
+
+def _quad_reduce_backward(ctx, grad_out):
+    (dx,) = ctx.saved_tensors
+    grad = dx.unsqueeze(-1) * grad_out.unsqueeze(1)  # (N,q,m)
+    shape = ctx.shape
+    if shape[1] == 1 and grad.shape[1] != 1:
+        grad = grad.sum(1, keepdim=True)
+    if shape[0] == 1 and grad.shape[0] != 1:
+        grad = grad.sum(0, keepdim=True)
+    return grad, None
+
+
+quad_reduce.register_autograd(_quad_reduce_backward, setup_context=_quad_reduce_setup)
+
+
+@torch.library.custom_op(f"{NS}::scatter", mutates_args=())
+def scatter(local: Tensor, seg: Tensor, perm: Tensor, inverse: Tensor) -> Tensor:
+    """out[p] = sum_{s in seg[p]:seg[p+1]} local.flat[perm[s]] in increasing s (deterministic).
+
+    `inverse[k]` is the output entry that flat input k lands in (used by the adjoint)."""
+    device = check_cuda(local, seg, perm)
+    n_out = seg.shape[0] - 1
+    out = torch.empty((n_out,), dtype=local.dtype, device=device)
+    call("tfem_scatter_bilinear", local.dtype, device, n_out, ptr(seg), ptr(perm), ptr(local), ptr(out))
+    return out
+
+
+@scatter.register_fake
+def _(local, seg, perm, inverse):
+    return local.new_empty((seg.shape[0] - 1,))
+
+
+@torch.library.custom_op(f"{NS}::gather", mutates_args=())
+def gather(src: Tensor, idx: Tensor) -> Tensor:
+    """buf[i] = src[idx[i]] (the interface pack kernel; also the adjoint of `scatter`)."""
+    device = check_cuda(src, idx)
+    out = torch.empty((idx.shape[0],), dtype=src.dtype, device=device)
+    call("tfem_iface_pack", src.dtype, device, idx.shape[0], ptr(idx), ptr(src), ptr(out))
+    return out
+
+
+@gather.register_fake
+def _(src, idx):
+    return src.new_empty((idx.shape[0],))
+
+
+def _scatter_setup(ctx, inputs, output):
+    local, seg, perm, inverse = inputs
+    ctx.save_for_backward(inverse)
+    ctx.shape = local.shape
+
+
+def _scatter_backward(ctx, grad_out):
+    (inverse,) = ctx.saved_tensors
+    return gather(grad_out.contiguous(), inverse).reshape(ctx.shape), None, None, None
+
+
+scatter.register_autograd(_scatter_backward, setup_context=_scatter_setup)
+
+
+@torch.library.custom_op(f"{NS}::unpack_add_", mutates_args=("dst",))
+def unpack_add_(dst: Tensor, idx: Tensor, buf: Tensor) -> None:
+    """dst[idx[i]] += buf[i] for unique idx (owner-side sum of interface rows)."""
+    device = check_cuda(dst, idx, buf)
+    call("tfem_iface_unpack_add", dst.dtype, device, idx.shape[0], ptr(idx), ptr(buf), ptr(dst))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused named forms
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op(f"{NS}::local_forms", mutates_args=())
+def local_forms(
+    coords: Tensor,
+    conn: Tensor,
+    n_el_per_mesh: int,
+    n_vert_per_mesh: int,
+    quad_order: int,
+    alpha: float,
+    beta: float,
+    want_matrix: bool,
+    source_kind: int,
+    source_p: List[float],
+    f_q: Optional[Tensor] = None,
+    frac_jac: Optional[Tensor] = None,
+    frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+    frac_t: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor]:
+    """Per-element alpha*K + beta*M (N,3,3) and load (N,3) without intermediates."""
+    device = check_cuda(coords, conn, f_q, frac_jac, frac_inv, frac_det, frac_t)
+    _nq_tri(quad_order)
+    n_el = conn.shape[0]
+    opts = dict(dtype=coords.dtype, device=device)
+    want_vec = source_kind != _lib.TFEM_SRC_NONE
+    local_mat = torch.empty((n_el, 3, 3) if want_matrix else (0, 3, 3), **opts)
+    local_vec = torch.empty((n_el, 3) if want_vec else (0, 3), **opts)
+    form = Bilinear(alpha, beta)
+    src = make_source(source_kind, source_p)
+    call(
+        "tfem_tri_p1_local_forms", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+        quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(frac_t), form, src, ptr(f_q),
+        ptr(local_mat) if want_matrix else None, ptr(local_vec) if want_vec else None,
+    )
+    return local_mat, local_vec
+
+
+@local_forms.register_fake
+def _(coords, conn, n_el_per_mesh, n_vert_per_mesh, quad_order, alpha, beta, want_matrix, source_kind, source_p,
+      f_q=None, frac_jac=None, frac_inv=None, frac_det=None, frac_t=None):
+    n_el = conn.shape[0]
+    return coords.new_empty((n_el if want_matrix else 0, 3, 3)), coords.new_empty((n_el if source_kind else 0, 3))
+
+
+def assemble_csr_tiled(plan, coords: Tensor, quad_order: int, alpha: float, beta: float, source_kind: int,
+                       source_p, csr_val: Optional[Tensor], load: Optional[Tensor]) -> None:
+    """Thin launcher of tfem_tri_p1_assemble_csr into preallocated outputs (one kernel)."""
+    device = check_cuda(coords, csr_val, load)
+    form = Bilinear(alpha, beta)
+    src = make_source(source_kind, source_p)
+    call("tfem_tri_p1_assemble_csr", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(csr_val), ptr(load))
+
+
+# ------------------------------------------------------------------------------------------------
+# weak residual with autograd
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op(f"{NS}::weak_residual_local", mutates_args=())
+def weak_residual_local(
+    grad_u: Tensor,
+    coords: Tensor,
+    conn: Tensor,
+    dof_conn: Tensor,
+    n_el_per_mesh: int,
+    n_vert_per_mesh: int,
+    quad_order: int,
+    source_kind: int,
+    source_p: List[float],
+    f_q: Optional[Tensor] = None,
+    frac_jac: Optional[Tensor] = None,
+    frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+    frac_t: Optional[Tensor] = None,
+) -> Tensor:
+    """grad_u (N,q,d) -> per-element residual (N,3): sum_q dx (f phi_i - grad phi_i . grad_u)."""
+    device = check_cuda(grad_u, coords, conn, dof_conn, f_q, frac_jac, frac_inv, frac_det, frac_t)
+    n_q = _nq_tri(quad_order)
+    n_el = conn.shape[0]
+    d = 3 if frac_inv is not None else 2
+    if tuple(grad_u.shape) != (n_el, n_q, d):
+        raise TfemError(f"grad_u must have shape {(n_el, n_q, d)}, got {tuple(grad_u.shape)}")
+    out = torch.empty((n_el, 3), dtype=coords.dtype, device=device)
+    src = make_source(source_kind, source_p)
+    call(
+        "tfem_weak_residual_local", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+        quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(frac_t), src, ptr(f_q), ptr(grad_u), ptr(out),
+    )
+    return out
+
+
+@weak_residual_local.register_fake
+def _(grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind, source_p,
+      f_q=None, frac_jac=None, frac_inv=None, frac_det=None, frac_t=None):
+    return coords.new_empty((conn.shape[0], 3))
+
+
+@torch.library.custom_op(f"{NS}::weak_residual_bwd", mutates_args=())
+def weak_residual_bwd(
+    r_bar: Tensor,
+    coords: Tensor,
+    conn: Tensor,
+    dof_conn: Tensor,
+    n_el_per_mesh: int,
+    n_vert_per_mesh: int,
+    quad_order: int,
+    frac_jac: Optional[Tensor] = None,
+    frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+) -> Tensor:
+    """r_bar (n_dof,) -> grad_u_bar (N,q,d) = -dx * sum_i grad phi_i * r_bar[dof_conn[:,i]]."""
+    device = check_cuda(r_bar, coords, conn, dof_conn, frac_jac, frac_inv, frac_det)
+    n_q = _nq_tri(quad_order)
+    n_el = conn.shape[0]
+    d = 3 if frac_inv is not None else 2
+    out = torch.empty((n_el, n_q, d), dtype=coords.dtype, device=device)
+    call(
+        "tfem_weak_residual_bwd", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+        ptr(dof_conn), quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(r_bar), ptr(out),
+    )
+    return out
+
+
+@weak_residual_bwd.register_fake
+def _(r_bar, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, frac_jac=None, frac_inv=None, frac_det=None):
+    d = 3 if frac_inv is not None else 2
+    return coords.new_empty((conn.shape[0], TRI_NQ[quad_order], d))
+
+
+@torch.library.custom_op(f"{NS}::weak_residual", mutates_args=())
+def weak_residual(
+    grad_u: Tensor,
+    coords: Tensor,
+    conn: Tensor,
+    dof_conn: Tensor,
+    lin_seg: Tensor,
+    lin_perm: Tensor,
+    n_el_per_mesh: int,
+    n_vert_per_mesh: int,
+    quad_order: int,
+    source_kind: int,
+    source_p: List[float],
+    f_q: Optional[Tensor] = None,
+    frac_jac: Optional[Tensor] = None,
+    frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None,
+    frac_t: Optional[Tensor] = None,
+) -> Tensor:
+    """Global weak residual r (n_dof,): element kernel + deterministic scatter, two launches."""
+    local = weak_residual_local(
+        grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind, source_p,
+        f_q, frac_jac, frac_inv, frac_det, frac_t,
+    )
+    device = check_cuda(local, lin_seg, lin_perm)
+    n_dof = lin_seg.shape[0] - 1
+    out = torch.empty((n_dof,), dtype=local.dtype, device=device)
+    call("tfem_scatter_linear", local.dtype, device, n_dof, ptr(lin_seg), ptr(lin_perm), ptr(local), ptr(out))
+    return out
+
+
+@weak_residual.register_fake
+def _(grad_u, coords, conn, dof_conn, lin_seg, lin_perm, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind,
+      source_p, f_q=None, frac_jac=None, frac_inv=None, frac_det=None, frac_t=None):
+    return coords.new_empty((lin_seg.shape[0] - 1,))
+
+
+def _weak_residual_setup(ctx, inputs, output):
+    (grad_u, coords, conn, dof_conn, lin_seg, lin_perm, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind,
+     source_p, f_q, frac_jac, frac_inv, frac_det, frac_t) = inputs
+    ctx.save_for_backward(coords, conn, dof_conn, frac_jac, frac_inv, frac_det)
+    ctx.meta = (n_el_per_mesh, n_vert_per_mesh, quad_order)
+
+
+def _weak_residual_backward(ctx, r_bar):
+    coords, conn, dof_conn, frac_jac, frac_inv, frac_det = ctx.saved_tensors
+    n_el_per_mesh, n_vert_per_mesh, quad_order = ctx.meta
+    grad = weak_residual_bwd(
+        r_bar.contiguous(), coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, frac_jac, frac_inv, frac_det
+    )
+    return (grad,) + (None,) * 15
+
+
+weak_residual.register_autograd(_weak_residual_backward, setup_context=_weak_residual_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# interpolation / jump
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op(f"{NS}::interp_cells", mutates_args=())
+def interp_cells(u: Tensor, dof_conn: Tensor, v_grad: Tensor, quad_order: int) -> Tuple[Tensor, Tensor]:
+    """u (n_dof,), dof_conn (N,3), v_grad (N,3,d) -> values (N,q), gradients (N,d)."""
+    device = check_cuda(u, dof_conn, v_grad)
+    n_q = _nq_tri(quad_order)
+    n_el, _, d = v_grad.shape
+    val = torch.empty((n_el, n_q), dtype=u.dtype, device=device)
+    grad = torch.empty((n_el, d), dtype=u.dtype, device=device)
+    call("tfem_interp_cells", u.dtype, device, n_el, ptr(dof_conn), ptr(v_grad), d, quad_order, ptr(u), ptr(val), ptr(grad))
+    return val, grad
+
+
+@interp_cells.register_fake
+def _(u, dof_conn, v_grad, quad_order):
+    return u.new_empty((v_grad.shape[0], TRI_NQ[quad_order])), u.new_empty((v_grad.shape[0], v_grad.shape[2]))
+
+
+@torch.library.custom_op(f"{NS}::interp_edges", mutates_args=())
+def interp_edges(
+    u: Tensor,
+    edge_cells: Tensor,
+    conn: Tensor,
+    first_vertex: Tensor,
+    inv_jac: Tensor,
+    x_q: Tensor,
+    n_edge_per_mesh: int,
+    n_el_per_mesh: int,
+) -> Tuple[Tensor, Tensor]:
+    """Both cells of every interior edge at the edge points: values (E,2,q), gradients (E,2,d)."""
+    device = check_cuda(u, edge_cells, conn, first_vertex, inv_jac, x_q)
+    n_edge, n_q, d = x_q.shape
+    val = torch.empty((n_edge, 2, n_q), dtype=u.dtype, device=device)
+    grad = torch.empty((n_edge, 2, d), dtype=u.dtype, device=device)
+    call(
+        "tfem_interp_edges", u.dtype, device, n_edge, n_edge_per_mesh, n_el_per_mesh, ptr(edge_cells), ptr(conn),
+        ptr(first_vertex), ptr(inv_jac), d, ptr(x_q), n_q, ptr(u), ptr(val), ptr(grad),
+    )
+    return val, grad
+
+
+@interp_edges.register_fake
+def _(u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh):
+    n_edge, n_q, d = x_q.shape
+    return u.new_empty((n_edge, 2, n_q)), u.new_empty((n_edge, 2, d))
+
+
+@torch.library.custom_op(f"{NS}::edge_jump", mutates_args=())
+def edge_jump(grad_edges: Tensor, normals: Tensor, h_e: Tensor, dx: Tensor) -> Tensor:
+    """eta_E = sum_q dx h_E (grad u+ . n + grad u- . (-n))^2; grad_edges (E,2,d) -> (E,)."""
+    device = check_cuda(grad_edges, normals, h_e, dx)
+    n_edge, _, d = grad_edges.shape
+    eta = torch.empty((n_edge,), dtype=grad_edges.dtype, device=device)
+    call("tfem_edge_jump", grad_edges.dtype, device, n_edge, d, dx.shape[1], ptr(grad_edges), ptr(normals), ptr(h_e), ptr(dx), ptr(eta))
+    return eta
+
+
+@edge_jump.register_fake
+def _(grad_edges, normals, h_e, dx):
+    return grad_edges.new_empty((grad_edges.shape[0],))
+
+
+# ------------------------------------------------------------------------------------------------
+# device policy
+# ------------------------------------------------------------------------------------------------
+
+SRC_NONE, SRC_SAMPLED, SRC_CONST, SRC_SINSIN = (
+    _lib.TFEM_SRC_NONE,
+    _lib.TFEM_SRC_SAMPLED,
+    _lib.TFEM_SRC_CONST,
+    _lib.TFEM_SRC_SINSIN,
+)
+
+
+def place_mesh(mesh):
+    """The assembly path is CUDA-only: move a host mesh to the current GPU or fail loudly."""
+    if mesh.device.type == "cuda":
+        return mesh
+    if not torch.cuda.is_available():
+        raise TfemError(
+            "pytorch_fem_solver_b200 needs a CUDA device: the element-assembly path has no CPU implementation"
+        )
+    _lib.load()  # fail now, not at the first integrate_* call, if the library is missing
+    return mesh.to(torch.device("cuda", torch.cuda.current_device()))

@@ -1,0 +1,64 @@
+"""Host-side symbolic phase (CSR pattern, permutation, tile plan) against the oracle; CPU only."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fem_oracle as fo
+from pytorch_fem_solver_b200 import csr, meshgen
+from tests.plan_emulator import emulate_tiled
+
+
+def meshes():
+    yield "structured4x4", meshgen.structured_rectangle(4, 4, topology=False)
+    yield "structured37x21_jitter", meshgen.structured_rectangle(37, 21, jitter=0.25, seed=2, topology=False)
+    yield "delaunay200", meshgen.delaunay_unit_square(200, seed=4)
+    yield "permuted", meshgen.permute_mesh(meshgen.structured_rectangle(24, 24, jitter=0.2, topology=False))
+
+
+@pytest.mark.parametrize("name,mesh", list(meshes()))
+def test_pattern_matches_oracle(name, mesh):
+    conn = mesh["triangles"]
+    n_dof = mesh["vertices"].shape[0]
+    crow, col, perm, seg = fo.csr_pattern(conn, n_dof)
+    pat = csr.build_pattern(torch.from_numpy(conn), n_dof)
+    assert np.array_equal(pat.crow.numpy(), crow) and np.array_equal(pat.col.numpy(), col)
+    assert np.array_equal(pat.perm.numpy(), perm) and np.array_equal(pat.seg.numpy(), seg)
+    rows, cols, form = csr.coo_index_maps(torch.from_numpy(conn))
+    o_rows, o_cols, o_form = fo.coo_index_maps(conn)
+    assert np.array_equal(rows.numpy(), o_rows) and np.array_equal(cols.numpy(), o_cols)
+    assert np.array_equal(form.numpy(), o_form)
+    # linear map: lin_perm groups the flat linear_form_idx by DOF, stably
+    lp, ls = pat.lin_perm.numpy(), pat.lin_seg.numpy()
+    assert np.array_equal(o_form[lp], np.sort(o_form, kind="stable"))
+    assert ls[-1] == 3 * conn.shape[0] and np.all(np.diff(lp.reshape(-1)[ls[5] : ls[6]]) > 0)
+
+
+def test_kat_pattern_4x4():
+    mesh = meshgen.structured_rectangle(4, 4, topology=False)
+    pat = csr.build_pattern(torch.from_numpy(mesh["triangles"]), 25)
+    assert pat.nnz == 137  # structural, not numeric (105): SURVEY.md 8(c)
+    assert pat.crow[:7].tolist() == [0, 4, 9, 14, 19, 22, 27]
+
+
+@pytest.mark.parametrize("name,mesh", list(meshes()))
+@pytest.mark.parametrize("rows_per_tile,ordering", [(8, "block"), (16, "morton"), (7, "natural"), (256, "block")])
+def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
+    coords, conn = mesh["vertices"], mesh["triangles"]
+    n_dof = coords.shape[0]
+    tconn = torch.from_numpy(conn)
+    pat = csr.build_pattern(tconn, n_dof)
+    plan = csr.build_tile_plan(tconn, tconn, pat, torch.from_numpy(coords), rows_per_tile, ordering)
+    assert plan.halo_factor >= 1.0
+    geo = fo.tri_geometry(coords, conn, 3)
+    local = fo.quad_reduce(fo.form_stiffness_mass(geo), geo["dx"])
+    f_q = fo.source_sinsin(geo["integration_points"])
+    lvec = fo.quad_reduce(fo.form_load(geo, f_q), geo["dx"]).reshape(-1, 3)
+    vals, load = emulate_tiled(plan, coords, local, lvec, conn, pat.nnz, n_dof)
+    crow, col, ref_vals = fo.scatter_bilinear_csr(local, conn, n_dof)
+    ref_load = fo.scatter_linear(lvec, conn, n_dof).reshape(-1)
+    assert not np.isnan(vals).any() and not np.isnan(load).any()
+    np.testing.assert_allclose(vals, ref_vals, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(load, ref_load, rtol=1e-13, atol=1e-15)
+    # every row is owned by exactly one tile
+    assert sorted(plan.row_id.tolist()) == list(range(n_dof))
