@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Headline benchmark: P1 stiffness+mass and load assembly to CSR (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full assembly of the synthetic structured mesh (nx=2048, ny=1024 squares ->
+4 194 304 triangles per GPU, fp64, 4-point quadrature, bilinear form grad u.grad v + u v and
+load f = 2 pi^2 sin(pi x) sin(pi y)) into CSR values + load vector.  Prints ONE JSON line.
+
+* `value`     elements/s, device-timed (CUDA events around every step, L2 flushed in between),
+              inputs resident in HBM, max over ranks;
+* `e2e`       the same through the public API with HOST buffers: pinned coordinates copied
+              host->device, assembly, CSR values + load copied device->host, every step;
+* `roofline`  algorithmic bytes (12 N_e + 16 N_v + 8 nnz + 8 N_v) / kernel time
+              against the measured HBM copy bandwidth of MEASURED_PEAKS.json;
+* `cpu_baseline`  the reference's own tensor program (oracle/torch_cpu_port.py) on the host cores.
+
+`--impl reference` times that CPU port alone (the reference is pure Python and does not exist on
+the GPU box).  Multi-GPU (`torchrun`, one rank per GPU): weak scaling, each rank
+assembles its own 4.19 M-element strip of a mesh that is N times taller, interface rows are
+summed over NCCL.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+NX, NY = 2048, 1024
+QUAD_ORDER = 3
+METRIC = "elements assembled/sec to CSR (P1, fp64)"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--nx", type=int, default=NX)
+    p.add_argument("--ny", type=int, default=NY)
+    p.add_argument("--path", default="tiled", choices=["tiled", "two_pass"])
+    p.add_argument("--rows-per-tile", type=int, default=256)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_event = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            names = {
+                "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            getter = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop_event.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                mask = getter(handle)
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as exc:  # NVML missing: report it, never fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def stop(self):
+        self._stop_event.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        ordered = sorted(self.samples)
+        return {"sm_mhz": ordered[len(ordered) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(ordered)}
+
+
+def cpu_reference_run(nx, ny, repeats=1):
+    """Time the CPU port of the reference pipeline; returns (elements/s, description, timings)."""
+    import torch
+
+    from oracle.torch_cpu_port import reference_assembly_cpu
+    from pytorch_fem_solver_b200 import meshgen
+
+    small = meshgen.structured_rectangle(64, 64, jitter=0.25, topology=False)
+    reference_assembly_cpu(torch.from_numpy(small["vertices"]), torch.from_numpy(small["triangles"]), QUAD_ORDER)
+    mesh = meshgen.structured_rectangle(nx, ny, jitter=0.25, seed=1234, topology=False)
+    coords, conn = torch.from_numpy(mesh["vertices"]), torch.from_numpy(mesh["triangles"])
+    best, best_t = None, None
+    for _ in range(repeats):
+        timings = {}
+        reference_assembly_cpu(coords, conn, QUAD_ORDER, timings)
+        if best is None or timings["total"] < best:
+            best, best_t = timings["total"], timings
+    n_el = conn.shape[0]
+    return n_el / best, f"{n_el} elements (nx={nx}, ny={ny}), best of {repeats}", {k: round(v, 4) for k, v in best_t.items()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    # bounded sample of the same workload: a quarter-height strip keeps a step near one second
+    nx, ny = args.nx, max(args.ny // 4, 1)
+    from oracle.torch_cpu_port import reference_assembly_cpu
+    from pytorch_fem_solver_b200 import meshgen
+
+    mesh = meshgen.structured_rectangle(nx, ny, jitter=0.25, seed=1234, topology=False)
+    coords, conn = torch.from_numpy(mesh["vertices"]), torch.from_numpy(mesh["triangles"])
+    n_el = conn.shape[0]
+    for _ in range(args.warmup):
+        reference_assembly_cpu(coords, conn, QUAD_ORDER)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_assembly_cpu(coords, conn, QUAD_ORDER)
+    elapsed = time.perf_counter() - t0
+    value = n_el * args.steps / elapsed
+    cores = torch.get_num_threads()
+    sample = f"{n_el} of {2 * args.nx * args.ny} elements per step (nx={nx}, ny={ny})"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "elements/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        "workload": f"BASELINE config 2: structured unit-square P1 triangle mesh nx={args.nx} ny={args.ny} per GPU "
+        f"({2 * args.nx * args.ny} elements), interior vertices jittered U(-0.25h,0.25h) seed 1234, fp64, "
+        "ElementTri(1,3) 4-point quadrature, grad u.grad v + u v to CSR values + load 2pi^2 sin(pi x) sin(pi y)",
+        "elements_per_gpu": 2 * args.nx * args.ny,
+        "path": args.path,
+        "l2": "flushed between timed steps (256 MiB write)",
+        "symbolic": "CSR pattern + tile plan built once, outside the timed region",
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import pytorch_fem_solver_b200 as tfem
+    from pytorch_fem_solver_b200 import _lib, forms, ops
+
+    torch.set_default_dtype(torch.float64)
+    bilinear, load_form = forms.StiffnessMass(1.0, 1.0), forms.Load(forms.SinSinSource())
+
+    if world == 1:
+        mesh_dict = tfem.meshgen.structured_rectangle(args.nx, args.ny, jitter=0.25, seed=1234, topology=False)
+        with torch.device(device):
+            basis = tfem.Basis(tfem.MeshTri(mesh_dict), tfem.ElementTri(1, QUAD_ORDER))
+        assembler = None
+    else:
+        from pytorch_fem_solver_b200 import distributed
+
+        assembler = distributed.StripAssembly(args.nx, args.ny, rank, world, device, QUAD_ORDER, rows_per_tile=args.rows_per_tile)
+        basis = assembler.basis
+        mesh_dict = assembler.mesh_dict
+
+    pat = basis.pattern
+    lay = basis._layout
+    n_el, n_v, nnz = lay.n_total, pat.n_dof, pat.nnz
+    src = load_form.source
+    values = torch.empty(nnz, dtype=torch.float64, device=device)
+    load = torch.empty(n_v, dtype=torch.float64, device=device)
+    if args.path == "tiled":
+        plan = basis.tile_plan(args.rows_per_tile)
+        plan_struct = plan.c_struct()
+
+        def local_step():
+            ops.assemble_csr_tiled(plan_struct, lay.coords, QUAD_ORDER, 1.0, 1.0, src.kind, src.params, values, load)
+
+        kernels_per_step = 1
+    else:
+        plan = None
+
+        def local_step():
+            basis._assemble_fused(bilinear, src, "two_pass")
+
+        kernels_per_step = 3
+
+    if assembler is not None:
+
+        def step():
+            local_step()
+            assembler.exchange(values, load)
+
+    else:
+        step = local_step
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- device-timed steps (value) ------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches_before = sum(_lib.LAUNCHES.values())
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(float(i))  # evict L2 (126 MB) between timed steps; outside the event pair
+        if world > 1:
+            dist.barrier()
+        starts[i].record()
+        step()
+        ends[i].record()
+    barrier()
+    gpu_launches = sum(_lib.LAUNCHES.values()) - launches_before
+    times_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = sum(times_ms)
+    clocks = sampler.stop()
+
+    # kernel-only time of the dominant kernel (roofline numerator), same stream, same flush
+    k_ms = []
+    for i in range(min(args.steps, 20)):
+        flush.fill_(float(i))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        local_step()
+        e.record()
+        e.synchronize()
+        k_ms.append(s.elapsed_time(e))
+    kernel_ms = sum(k_ms) / len(k_ms)
+
+    # ---- end-to-end through the public API with host buffers (e2e) ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        coords_host = torch.from_numpy(mesh_dict["vertices"]).pin_memory()
+        values_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        load_host = torch.empty((n_v, 1), dtype=torch.float64).pin_memory()
+
+        if assembler is not None:
+            basis._post_assemble_hook = assembler.exchange  # interface rows summed before the device->host copy
+
+        def e2e_step():
+            basis.assemble_from_host(coords_host, bilinear, load_form, values_host, load_host, path=args.path)
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e2e_steps = max(min(args.steps, 20), 1)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {"seconds": e2e_s, "steps": e2e_steps, "h2d": coords_host.numel() * 8, "d2h": (values_host.numel() + load_host.numel()) * 8}
+
+    # ---- reduce over ranks -----------------------------------------------------------------------
+    stats = torch.tensor([total_ms, kernel_ms, e2e["seconds"] / e2e["steps"] if e2e else 0.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms, e2e_step_s = stats.tolist()
+    total_elements = n_el * world
+
+    if rank == 0:
+        peak, peak_source = measured_peak()
+        algorithmic = 12 * n_el + 16 * n_v + 8 * nnz + 8 * n_v
+        achieved = algorithmic / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC,
+            "value": total_elements * args.steps / (total_ms * 1e-3),
+            "unit": "elements/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "gpu_launches": gpu_launches,
+            "roofline": {
+                "bound": "hbm",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": peak_source,
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "kernel": "assemble_tiled_kernel<double,256,true,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
+                "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": algorithmic,
+                "bytes_per_element": algorithmic / n_el,
+            },
+        }
+        if plan is not None:
+            line["config"]["tile_plan"] = {"tiles": plan.n_tiles, "rows_per_tile": args.rows_per_tile, "halo_factor": round(plan.halo_factor, 4),
+                                           "index_bytes": plan.index_bytes, "max_vert": plan.max_vert, "max_elem": plan.max_elem, "max_out": plan.max_out}
+        if e2e:
+            line["e2e"] = {
+                "value": total_elements / e2e_step_s,
+                "unit": "elements/s",
+                "h2d_bytes_per_step": e2e["h2d"],
+                "d2h_bytes_per_step": e2e["d2h"],
+                "ms_per_step": e2e_step_s * 1e3,
+                "api": "Basis.assemble_from_host(pinned coords, StiffnessMass, Load, pinned values, pinned load)",
+            }
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_value, sample, timings = cpu_reference_run(args.nx, args.ny, repeats=2)
+            line["cpu_baseline"] = {"value": cpu_value, "unit": "elements/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": sample, "host_cpus": os.cpu_count(), "stage_seconds": timings}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

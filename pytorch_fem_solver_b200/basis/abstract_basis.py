@@ -241,6 +241,27 @@ class AbstractBasis(abc.ABC):
             self._vector_result(vec) if vec is not None else None,
         )
 
+    def assemble_from_host(self, coords_host: torch.Tensor, bilinear, load, values_out: Optional[torch.Tensor],
+                           load_out: Optional[torch.Tensor], path: str = "auto"):
+        """Re-assemble for new vertex coordinates held in (pinned) HOST memory.
+
+        Copies `coords_host` over the basis' device coordinates, runs the fused assembly and copies
+        the CSR value array / load vector back into the given host tensors; everything is enqueued
+        on the current stream (synchronise before reading the outputs).  The mesh topology -- and
+        with it the CSR pattern and tile plan -- is unchanged, so nothing symbolic is redone."""
+        lay = self._layout
+        lay.coords.copy_(coords_host.reshape(lay.coords.shape), non_blocking=True)
+        self._geometry = None  # cached v_grad / points / dx belong to the old coordinates
+        values, vec = self._assemble_fused(bilinear, load.source if load is not None else None, path)
+        hook = getattr(self, "_post_assemble_hook", None)
+        if hook is not None:
+            hook(values, vec)
+        if values_out is not None and values is not None:
+            values_out.copy_(values, non_blocking=True)
+        if load_out is not None and vec is not None:
+            load_out.copy_(vec.reshape(load_out.shape), non_blocking=True)
+        return values_out, load_out
+
     def _assemble_fused(self, bilinear, source, path: str = "auto"):
         lay = self._layout
         pat = self.pattern

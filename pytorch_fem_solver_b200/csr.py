@@ -71,8 +71,11 @@ def _coo_keys(conn: torch.Tensor, n_dof: int) -> torch.Tensor:
     return rows.long() * n_dof + cols.long()
 
 
-def build_pattern(dof_conn: torch.Tensor, n_dof: int) -> CsrPattern:
-    """Sorted-unique CSR pattern + stable permutation of the 9*n_el COO entries."""
+def build_pattern(dof_conn: torch.Tensor, n_dof: int, extra_keys: torch.Tensor | None = None) -> CsrPattern:
+    """Sorted-unique CSR pattern + stable permutation of the 9*n_el COO entries.
+
+    `extra_keys` (row*n_dof+col) adds structural entries that receive no local contribution;
+    the multi-GPU owner of an interface row uses them for columns only other ranks touch."""
     conn = dof_conn.reshape(-1, 3).contiguous()
     n_el = conn.shape[0]
     if 9 * n_el >= 2**31:
@@ -81,6 +84,12 @@ def build_pattern(dof_conn: torch.Tensor, n_dof: int) -> CsrPattern:
     keys = _coo_keys(conn.to(torch.int32) if conn.is_cuda else conn, n_dof)
     sorted_keys, perm = torch.sort(keys, stable=True)
     uniq, counts = torch.unique_consecutive(sorted_keys, return_counts=True)
+    if extra_keys is not None and extra_keys.numel():
+        # structural entries with no local contribution (rows completed by other ranks)
+        merged = torch.unique(torch.cat([uniq, extra_keys.to(uniq)]))
+        merged_counts = torch.zeros(merged.shape[0], dtype=counts.dtype, device=device)
+        merged_counts[torch.searchsorted(merged, uniq)] = counts
+        uniq, counts = merged, merged_counts
     nnz = int(uniq.shape[0])
     seg = torch.zeros(nnz + 1, dtype=torch.int64, device=device)
     seg[1:] = torch.cumsum(counts, 0)

@@ -1,0 +1,210 @@
+"""Element-partitioned multi-GPU assembly: one process per GPU, interface rows summed over NCCL.
+
+SURVEY.md section 8(e).  Elements are split across ranks; every rank assembles its own elements into
+a local CSR with the same deterministic kernels as the single-GPU path.  A global row (DOF) that
+is touched by elements of several ranks is OWNED by the lowest such rank; the other ranks send
+their partial row sums (matrix entries and load entry) to the owner, which adds them in fixed
+rank order.  Only those interface rows travel: for horizontal strips of the config-2 mesh that is
+one vertex row (~14 k matrix entries + 2 k load entries, ~130 KB) per cut.
+
+Set-up (integer, one-time, `torch.distributed` collectives on index tensors):
+  1. owner / multiplicity of every global vertex by all-reduce(MIN / SUM);
+  2. every rank tells each owner which (row, col) keys it will contribute; the owner adds columns
+     it does not touch itself as ghost DOFs so its rows carry the full global pattern;
+  3. both sides translate the agreed key list into positions in their own CSR value arrays.
+Per assembly: pack (tfem_iface_pack) -> batched isend/irecv -> unpack-add (tfem_iface_unpack_add).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import csr as csr_mod
+
+
+@dataclass
+class ExchangeOps:
+    """How interface entries are gathered / accumulated (CUDA kernels in production)."""
+
+    pack: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]  # (src, idx) -> src[idx]
+    unpack_add: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]  # dst[idx] += buf
+
+
+def cuda_exchange_ops() -> ExchangeOps:
+    from . import ops
+
+    return ExchangeOps(pack=ops.gather, unpack_add=ops.unpack_add_)
+
+
+def _exchange_variable(send: Dict[int, torch.Tensor], rank: int, world: int, device, dtype, group) -> Dict[int, torch.Tensor]:
+    """Every rank sends `send[peer]` (1-D, any length) to `peer`; returns what each peer sent us."""
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    for peer, t in send.items():
+        counts[peer] = t.numel()
+    table = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(table, counts, group=group)
+    incoming = {peer: int(table[peer][rank]) for peer in range(world) if peer != rank and int(table[peer][rank]) > 0}
+    recv = {peer: torch.empty(n, dtype=dtype, device=device) for peer, n in incoming.items()}
+    ops_list = []
+    for peer in sorted(set(send) | set(recv)):
+        # lower rank sends first: a fixed global order keeps blocking back-ends deadlock-free
+        if peer in send and send[peer].numel() > 0:
+            ops_list.append(dist.P2POp(dist.isend, send[peer].contiguous(), peer, group=group))
+        if peer in recv:
+            ops_list.append(dist.P2POp(dist.irecv, recv[peer], peer, group=group))
+    if ops_list:
+        for work in dist.batch_isend_irecv(ops_list):
+            work.wait()
+    return recv
+
+
+class InterfacePlan:
+    """Who owns which rows and where interface contributions sit in the local arrays."""
+
+    def __init__(self, elem_global_conn: torch.Tensor, n_global: int, rank: int, world: int, group=None):
+        device = elem_global_conn.device
+        conn = elem_global_conn.reshape(-1, 3).long()
+        self.rank, self.world, self.group, self.n_global = rank, world, group, n_global
+
+        touched = torch.unique(conn)
+        owner = torch.full((n_global,), world, dtype=torch.int32, device=device)
+        owner[touched] = rank
+        dist.all_reduce(owner, op=dist.ReduceOp.MIN, group=group)
+        mult = torch.zeros(n_global, dtype=torch.int32, device=device)
+        mult[touched] = 1
+        dist.all_reduce(mult, op=dist.ReduceOp.SUM, group=group)
+        self.owner_of_touched = owner[touched]
+        self.interface_global = touched[mult[touched] > 1]
+
+        # keys (row, col) of our COO whose row belongs to another rank, per owner
+        rows = conn[:, [0, 1, 2, 0, 1, 2, 0, 1, 2]].reshape(-1)
+        cols = conn.repeat_interleave(3, dim=1).reshape(-1)
+        row_owner = owner[rows]
+        foreign = row_owner != rank
+        keys = torch.unique(rows[foreign] * n_global + cols[foreign])
+        key_owner = owner[torch.div(keys, n_global, rounding_mode="floor")]
+        self.send_keys = {int(o): keys[key_owner == o] for o in torch.unique(key_owner).tolist()}
+        self.recv_keys = _exchange_variable(self.send_keys, rank, world, device, torch.int64, group)
+
+        # ghost DOFs: columns of received keys that none of our own elements touches
+        ghosts = [torch.empty(0, dtype=torch.int64, device=device)]
+        for k in self.recv_keys.values():
+            c = k % n_global
+            ghosts.append(c[~torch.isin(c, touched)])
+        self.local_to_global = torch.unique(torch.cat([touched, *ghosts]))
+        self.n_local = int(self.local_to_global.numel())
+        self.n_ghost = self.n_local - int(touched.numel())
+        self.dof_conn = torch.searchsorted(self.local_to_global, conn).to(torch.int32)
+        self.owned_rows = owner[self.local_to_global] == rank  # rows complete on this rank after exchange
+        self.extra_keys = self._to_local_keys(torch.cat(list(self.recv_keys.values()))) if self.recv_keys else None
+
+    def _to_local_keys(self, global_keys: torch.Tensor) -> torch.Tensor:
+        r = torch.div(global_keys, self.n_global, rounding_mode="floor")
+        c = global_keys - r * self.n_global
+        return torch.searchsorted(self.local_to_global, r) * self.n_local + torch.searchsorted(self.local_to_global, c)
+
+    def bind(self, pattern: csr_mod.CsrPattern):
+        """Positions of every exchanged entry in this rank's CSR value / load arrays."""
+
+        def positions(global_keys):
+            local = self._to_local_keys(global_keys)
+            pos = torch.searchsorted(pattern.keys, local)
+            if not bool((pattern.keys[pos.clamp_max(pattern.nnz - 1)] == local).all()):
+                raise RuntimeError("interface key missing from the local CSR pattern")
+            rows_g = torch.unique(torch.div(global_keys, self.n_global, rounding_mode="floor"))
+            return pos.to(torch.int32), torch.searchsorted(self.local_to_global, rows_g).to(torch.int32)
+
+        self.send_idx = {peer: positions(k) for peer, k in self.send_keys.items()}
+        self.recv_idx = {peer: positions(k) for peer, k in self.recv_keys.items()}
+        return self
+
+
+class InterfaceExchange:
+    """Per-assembly exchange: pack -> isend/irecv -> unpack-add in ascending peer order."""
+
+    def __init__(self, plan: InterfacePlan, exchange_ops: Optional[ExchangeOps] = None):
+        self.plan = plan
+        self.ops = exchange_ops or cuda_exchange_ops()
+        self.bytes_sent = 0
+
+    def __call__(self, values: Optional[torch.Tensor], load: Optional[torch.Tensor]):
+        plan = self.plan
+        load_flat = load.reshape(-1) if load is not None else None
+        send_bufs, recv_bufs, p2p = {}, {}, []
+        for peer in sorted(set(plan.send_idx) | set(plan.recv_idx)):
+            if peer in plan.send_idx:
+                vi, ri = plan.send_idx[peer]
+                parts = []
+                if values is not None:
+                    parts.append(self.ops.pack(values, vi))
+                if load_flat is not None:
+                    parts.append(self.ops.pack(load_flat, ri))
+                send_bufs[peer] = torch.cat(parts)
+                self.bytes_sent += send_bufs[peer].numel() * send_bufs[peer].element_size()
+                p2p.append(dist.P2POp(dist.isend, send_bufs[peer], peer, group=plan.group))
+            if peer in plan.recv_idx:
+                vi, ri = plan.recv_idx[peer]
+                n = (vi.numel() if values is not None else 0) + (ri.numel() if load_flat is not None else 0)
+                ref = values if values is not None else load_flat
+                recv_bufs[peer] = torch.empty(n, dtype=ref.dtype, device=ref.device)
+                p2p.append(dist.P2POp(dist.irecv, recv_bufs[peer], peer, group=plan.group))
+        if p2p:
+            for work in dist.batch_isend_irecv(p2p):
+                work.wait()
+        for peer in sorted(recv_bufs):  # fixed order -> bitwise reproducible sums
+            vi, ri = plan.recv_idx[peer]
+            buf = recv_bufs[peer]
+            offset = 0
+            if values is not None:
+                self.ops.unpack_add(values, vi, buf[: vi.numel()].contiguous())
+                offset = vi.numel()
+            if load_flat is not None:
+                self.ops.unpack_add(load_flat, ri, buf[offset:].contiguous())
+
+
+def strip_mesh(nx: int, ny: int, rank: int, world: int, jitter: float = 0.25, seed: int = 1234):
+    """Rank `rank`'s horizontal strip of the `nx` x `ny*world` structured mesh on [0,1]x[0,world].
+
+    Returns (mesh dict in local numbering, global vertex id of local vertex 0, n_global)."""
+    from . import meshgen
+
+    mesh = meshgen.structured_rectangle(nx, ny, 0.0, 1.0, float(rank), float(rank + 1), jitter=jitter, seed=seed + rank, topology=False)
+    offset = rank * ny * (nx + 1)
+    n_global = (nx + 1) * (ny * world + 1)
+    return mesh, offset, n_global
+
+
+class StripAssembly:
+    """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip."""
+
+    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=256, group=None, exchange_ops=None):
+        import numpy as np
+
+        from . import ElementTri, MeshTri
+
+        mesh, offset, n_global = strip_mesh(nx, ny, rank, world)
+        conn_global = torch.from_numpy(mesh["triangles"].astype(np.int64) + offset).to(device)
+        self.plan = InterfacePlan(conn_global, n_global, rank, world, group)
+        if self.plan.n_ghost:
+            pad = np.zeros((self.plan.n_ghost, 2))
+            mesh["vertices"] = np.concatenate([mesh["vertices"], pad])
+            mesh["vertex_markers"] = np.concatenate([mesh["vertex_markers"], np.zeros((self.plan.n_ghost, 1), dtype=np.int32)])
+        self.mesh_dict = mesh
+        with torch.device(device):
+            self.basis = _basis_for(MeshTri(mesh), ElementTri(1, quad_order))
+        # strips are contiguous ranges of global ids, so local ids are global ids minus a constant
+        # and ghosts (the vertex row above the strip) sort to the end: local numbering is unchanged
+        assert torch.equal(self.plan.dof_conn.cpu(), torch.from_numpy(mesh["triangles"]).to(torch.int32))
+        self.basis._pattern = csr_mod.build_pattern(self.basis._dof_conn_flat(), self.plan.n_local, self.plan.extra_keys)
+        self.plan.bind(self.basis.pattern)
+        self.exchange = InterfaceExchange(self.plan, exchange_ops)
+
+
+def _basis_for(mesh, element):
+    from . import Basis
+
+    return Basis(mesh, element)

@@ -22,8 +22,8 @@ class Patches(MeshesTri):
         coordinates = centers.unsqueeze(-2) + signs * radius.unsqueeze(-2)  # (P,5,2)
         n_patches = coordinates.shape[0]
         c, s = math.cos(math.pi / 4), math.sin(math.pi / 4)
-        self.rotation_matrix = torch.tensor([[c, -s], [s, c]])
-        self.rotated_signs = (self.rotation_matrix @ signs.to(torch.get_default_dtype()).mT.cpu()).mT
+        self.rotation_matrix = torch.tensor([[c, -s], [s, c]], device=centers.device)
+        self.rotated_signs = (self.rotation_matrix @ signs.to(self.rotation_matrix.dtype).mT).mT
         # one stacked dict directly: no per-patch Python loop (the reference builds P dicts, :39-45)
         return {
             "vertices": coordinates,

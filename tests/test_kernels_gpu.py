@@ -1,0 +1,252 @@
+"""Kernel-level parity on the GPU against the oracle: precisions, edge cases, determinism and
+size-independent properties at the full BASELINE config-2 size.  `pytest -m gpu`."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_fem_solver_b200 as tfem
+from oracle import fem_oracle as fo
+from pytorch_fem_solver_b200 import forms, meshgen
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_basis(mesh_dict, order=3, dtype=torch.float64):
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        with torch.device(DEV):
+            return tfem.Basis(tfem.MeshTri(mesh_dict), tfem.ElementTri(1, order))
+    finally:
+        torch.set_default_dtype(previous)
+
+
+def oracle_system(mesh_dict, order=3, alpha=1.0, beta=1.0):
+    coords, conn = mesh_dict["vertices"], mesh_dict["triangles"]
+    geo = fo.tri_geometry(coords, conn, order)
+    local = fo.quad_reduce(alpha * fo.form_stiffness(geo) + beta * fo.form_mass(geo), geo["dx"])
+    crow, col, vals = fo.scatter_bilinear_csr(local, conn, coords.shape[0])
+    f_q = fo.source_sinsin(geo["integration_points"])
+    load = fo.scatter_linear(fo.quad_reduce(fo.form_load(geo, f_q), geo["dx"]), conn, coords.shape[0]).reshape(-1)
+    return crow, col, vals, load
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a) - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("path", ["tiled", "two_pass"])
+def test_fp64_matches_oracle_all_orders(order, path):
+    mesh = meshgen.structured_rectangle(40, 24, jitter=0.25, seed=order, topology=False)
+    basis = make_basis(mesh, order)
+    values, load = basis.assemble(forms.StiffnessMass(0.7, 1.3), forms.Load(), layout="values", path=path)
+    crow, col, ref_vals, ref_load = oracle_system(mesh, order, 0.7, 1.3)
+    assert np.array_equal(basis.pattern.crow.cpu().numpy(), crow)  # bit-exact pattern
+    assert np.array_equal(basis.pattern.col.cpu().numpy(), col)
+    assert relmax(values.cpu().numpy(), ref_vals) < 1e-12  # tolerance of BASELINE.json north_star (fp64)
+    assert relmax(load.cpu().numpy().reshape(-1), ref_load) < 1e-12
+
+
+@pytest.mark.parametrize("path", ["tiled", "two_pass"])
+def test_fp32_within_1e5_of_fp64_oracle(path):
+    # coarse mesh: in fp32 the edge vectors x1-x0 carry a relative error ~eps/h, so the stated
+    # 1e-5 tolerance is only meaningful while h is not small
+    mesh = meshgen.structured_rectangle(12, 10, jitter=0.2, seed=3, topology=False)
+    basis = make_basis(mesh, 3, torch.float32)
+    values, load = basis.assemble(forms.StiffnessMass(), forms.Load(), layout="values", path=path)
+    assert values.dtype == torch.float32
+    _, _, ref_vals, ref_load = oracle_system(mesh, 3)
+    assert relmax(values.double().cpu().numpy(), ref_vals) < 1e-5
+    assert relmax(load.double().cpu().numpy().reshape(-1), ref_load) < 1e-5
+
+
+def test_generic_path_fp32():
+    mesh = meshgen.delaunay_unit_square(40, seed=2)
+    basis = make_basis(mesh, 4, torch.float32)
+    a = basis.integrate_bilinear_form(lambda b: b.v_grad @ b.v_grad.mT + b.v @ b.v.mT, layout="values")
+    _, _, ref_vals, _ = oracle_system(mesh, 4)
+    assert relmax(a.double().cpu().numpy(), ref_vals) < 1e-5
+
+
+def test_clockwise_elements_keep_the_signed_determinant():
+    """element_tri.py:139 uses det J without abs(): clockwise cells contribute negative weights."""
+    mesh = meshgen.structured_rectangle(9, 7, jitter=0.2, seed=1, topology=False)
+    mesh["triangles"][::3] = mesh["triangles"][::3][:, [0, 2, 1]]
+    basis = make_basis(mesh, 3)
+    crow, col, ref_vals, ref_load = oracle_system(mesh, 3)
+    for path in ("tiled", "two_pass"):
+        values, load = basis.assemble(forms.StiffnessMass(), forms.Load(), layout="values", path=path)
+        assert relmax(values.cpu().numpy(), ref_vals) < 1e-12
+        assert relmax(load.cpu().numpy().reshape(-1), ref_load) < 1e-12
+    assert (ref_vals[crow[:-1]] < 0).any() or (ref_vals < 0).any()
+
+
+def test_isolated_vertices_and_single_triangle():
+    mesh = {
+        "vertices": np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [5.0, 5.0], [6.0, 6.0]]),
+        "triangles": np.array([[0, 1, 2]], dtype=np.int32),
+        "vertex_markers": np.ones((5, 1), dtype=np.int32),
+    }
+    basis = make_basis(mesh, 3)
+    crow, col, ref_vals, ref_load = oracle_system(mesh, 3)
+    assert basis.pattern.crow.tolist() == [0, 3, 6, 9, 9, 9]
+    for path in ("tiled", "two_pass"):
+        values, load = basis.assemble(forms.Stiffness(), forms.Load(forms.ConstSource(1.0)), layout="values", path=path)
+        k_loc = 0.5 * np.array([2.0, -1, -1, -1, 1, 0, -1, 0, 1])  # SURVEY.md 8(c) unit right triangle
+        np.testing.assert_allclose(values.cpu().numpy(), k_loc, atol=1e-15)
+        np.testing.assert_allclose(load.cpu().numpy().reshape(-1), [1 / 6, 1 / 6, 1 / 6, 0, 0], atol=1e-15)
+
+
+def test_empty_inputs_are_accepted():
+    from pytorch_fem_solver_b200 import ops
+
+    coords = torch.zeros((3, 2), dtype=torch.float64, device=DEV)
+    conn = torch.zeros((0, 3), dtype=torch.int32, device=DEV)
+    inv, vg, xq, dx = ops.tri_geometry(coords, conn, 1, 3, 2)
+    assert inv.shape == (0, 2, 2) and xq.shape == (0, 3, 2) and dx.shape == (0, 3)
+    out = ops.scatter(torch.zeros(0, dtype=torch.float64, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV),
+                      torch.zeros(0, dtype=torch.int32, device=DEV), torch.zeros(0, dtype=torch.int32, device=DEV))
+    assert out.shape == (0,)
+
+
+def test_unsupported_orders_raise_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        tfem.ElementTri(1, 5)
+    with pytest.raises(NotImplementedError):
+        tfem.ElementLine(1, 4)
+    mesh = meshgen.structured_rectangle(2, 2)
+    with pytest.raises(NotImplementedError):
+        make_basis_with_p2(mesh)
+
+
+def make_basis_with_p2(mesh):
+    with torch.device(DEV):
+        return tfem.Basis(tfem.MeshTri(mesh), tfem.ElementTri(2, 2))
+
+
+def test_bitwise_determinism():
+    mesh = meshgen.permute_mesh(meshgen.structured_rectangle(96, 64, jitter=0.25, topology=False))
+    basis = make_basis(mesh, 3)
+    runs = []
+    for _ in range(3):
+        for path in ("tiled", "two_pass"):
+            v, b = basis.assemble(forms.StiffnessMass(), forms.Load(), layout="values", path=path)
+            runs.append((path, v.clone(), b.clone()))
+    for path, v, b in runs[2:]:
+        first = runs[0] if path == "tiled" else runs[1]
+        assert torch.equal(v, first[1]) and torch.equal(b, first[2])
+    # both kernels add contributions in increasing element order, so they agree closely
+    assert relmax(runs[0][1].cpu().numpy(), runs[1][1].cpu().numpy()) < 1e-14
+
+
+def test_weak_residual_large_against_oracle():
+    mesh = meshgen.structured_rectangle(160, 120, jitter=0.25, seed=6, topology=False)
+    basis = make_basis(mesh, 4)
+    coords, conn = mesh["vertices"], mesh["triangles"]
+    geo = fo.tri_geometry(coords, conn, 4)
+    rng = np.random.default_rng(0)
+    grad = rng.standard_normal(geo["integration_points"].shape)
+    f_q = fo.source_sinsin(geo["integration_points"])
+    ref = fo.scatter_linear(fo.quad_reduce(fo.form_weak_residual(geo, f_q, grad), geo["dx"]), conn, coords.shape[0])
+    gu = torch.tensor(grad, device=DEV, requires_grad=True)
+    r = basis.integrate_linear_form(forms.WeakResidual(), gu)
+    assert relmax(r.detach().cpu().numpy(), ref) < 1e-12
+    cot = rng.standard_normal(ref.shape)
+    (r * torch.tensor(cot, device=DEV)).sum().backward()
+    ref_bar = fo.weak_residual_backward(geo, conn, cot)
+    assert relmax(gu.grad.cpu().numpy(), ref_bar) < 1e-12
+
+
+def test_patches_config3_size_fp32():
+    """BASELINE config 3 shape: 4096 patches, 6-point quadrature, fp32 weak residual."""
+    centers, radius = meshgen.generate_patches_info(6)
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        with torch.device(DEV):
+            patches = tfem.Patches(torch.tensor(centers, dtype=torch.float32), torch.tensor(radius, dtype=torch.float32))
+            basis = tfem.PatchesBasis(patches, tfem.ElementTri(1, 4))
+        coords = fo.patch_vertices(centers, radius)
+        conn = np.broadcast_to(fo.PATCH_CELLS, (4096, 4, 3))
+        geo = fo.tri_geometry(coords, conn, 4)
+        rng = np.random.default_rng(1)
+        grad = rng.standard_normal(geo["integration_points"].shape)
+        f_q = fo.source_sinsin(geo["integration_points"])
+        flat = (conn + 5 * np.arange(4096)[:, None, None]).reshape(-1, 3)
+        ref = fo.scatter_linear(fo.quad_reduce(fo.form_weak_residual(geo, f_q, grad), geo["dx"]), flat, 5 * 4096).reshape(4096, 5, 1)
+        r = basis.integrate_linear_form(forms.WeakResidual(), torch.tensor(grad, dtype=torch.float32, device=DEV))
+        assert r.shape == (4096, 5, 1)
+        assert relmax(r.double().cpu().numpy(), ref) < 1e-5
+        assert basis.reduce(r).shape == (4096, 1)
+    finally:
+        torch.set_default_dtype(previous)
+
+
+@pytest.fixture(scope="module")
+def config2():
+    mesh = meshgen.structured_rectangle(2048, 1024, jitter=0.25, seed=1234, topology=False)
+    return mesh, make_basis(mesh, 3)
+
+
+def test_config2_sizes(config2):
+    mesh, basis = config2
+    assert mesh["triangles"].shape[0] == 4194304 and mesh["vertices"].shape[0] == 2100225
+    assert basis.pattern.nnz == 14689281  # N_v + 2 (N_v + N_e - 1), SURVEY.md 8(d)
+
+
+def test_config2_properties(config2):
+    """Size-independent invariants at the full benchmark size (the oracle takes too long here)."""
+    mesh, basis = config2
+    pat = basis.pattern
+    rows = pat.row_indices()
+    m = basis.assemble(forms.Mass(), None, layout="values", path="tiled")[0]
+    assert abs(float(m.sum()) - 1.0) < 1e-12  # sum of the mass matrix = area of the unit square
+    k, load = basis.assemble(forms.Stiffness(), forms.Load(), layout="values", path="tiled")
+    row_sum = torch.zeros(pat.n_dof, dtype=torch.float64, device=DEV).index_add_(0, rows, k)
+    diag = k[torch.searchsorted(pat.keys, torch.arange(pat.n_dof, device=DEV) * (pat.n_dof + 1))]
+    assert float((row_sum.abs() / diag).max()) < 1e-11  # constants are in the kernel of the stiffness matrix
+    assert abs(float(load.sum()) - 8.0) < 1e-5  # int 2 pi^2 sin(pi x) sin(pi y) = 8, up to quadrature error
+    # symmetry of the assembled operator
+    transposed = torch.searchsorted(pat.keys, pat.col.long() * pat.n_dof + rows)
+    km = basis.assemble(forms.StiffnessMass(), None, layout="values", path="tiled")[0]
+    assert float((km - km[transposed]).abs().max() / km.abs().max()) < 1e-14
+    # two independent kernels agree
+    km2 = basis.assemble(forms.StiffnessMass(), None, layout="values", path="two_pass")[0]
+    assert float((km - km2).abs().max() / km.abs().max()) < 1e-14
+
+
+def test_config2_rows_against_oracle(config2):
+    """Exact oracle comparison on a band of rows of the 4M-element mesh."""
+    mesh, basis = config2
+    coords, conn = mesh["vertices"], mesh["triangles"]
+    band = 3 * 2049  # three vertex rows: all elements touching the first two are inside
+    sel = (conn < band).all(axis=1)
+    sub_conn = conn[sel]
+    geo = fo.tri_geometry(coords[:band], sub_conn, 3)
+    local = fo.quad_reduce(fo.form_stiffness_mass(geo), geo["dx"])
+    crow, col, vals = fo.scatter_bilinear_csr(local, sub_conn, band)
+    f_q = fo.source_sinsin(geo["integration_points"])
+    load_ref = fo.scatter_linear(fo.quad_reduce(fo.form_load(geo, f_q), geo["dx"]), sub_conn, band).reshape(-1)
+    values, load = basis.assemble(forms.StiffnessMass(), forms.Load(), layout="values", path="tiled")
+    full_rows = 2 * 2049
+    pat = basis.pattern
+    n = int(pat.crow[full_rows])
+    assert n == crow[full_rows]
+    assert np.array_equal(pat.col[:n].cpu().numpy(), col[:n])
+    assert relmax(values[:n].cpu().numpy(), vals[:n]) < 1e-12
+    assert relmax(load[:full_rows].cpu().numpy().reshape(-1), load_ref[:full_rows]) < 1e-12
+
+
+def test_geometry_config2_roundtrip(config2):
+    """x_q of the geometry kernel lie inside their triangles and dx sums to the area."""
+    _, basis = config2
+    assert abs(float(basis._dx.sum()) - 1.0) < 1e-12
+    assert float(basis._dx.sum(-3).min()) > 0.0  # the 4-point rule has one negative weight; areas are positive
+    pts = basis.integration_points
+    assert pts.shape == (4194304, 4, 1, 2)
+    assert float(pts.min()) >= 0.0 and float(pts.max()) <= 1.0

@@ -1,0 +1,31 @@
+"""Summarise an `ncu --page source --csv --print-source=sass` export: opcode mix and stall reasons.
+
+usage: python tools/ncu_sass_summary.py <file.csv> [top]
+"""
+import io
+import sys
+
+import pandas as pd
+
+
+def main(path, top=18):
+    lines = open(path).read().split("\n")
+    df = pd.read_csv(io.StringIO("\n".join(lines[1:])), dtype=str)
+    num = lambda c: pd.to_numeric(df[c], errors="coerce").fillna(0)  # noqa: E731
+    df["inst"] = num("Instructions Executed")
+    df["samples"] = num("# Samples")
+    src = df["Source"].str.strip().str.replace(r"^@!?U?P\d+\s+", "", regex=True)
+    df["op"] = src.str.split().str[0].str.split(".").str[0]
+    total = df["inst"].sum()
+    print(f"SASS lines {len(df)}  warp instructions {total:.0f}  samples {df['samples'].sum():.0f}")
+    g = df.groupby("op").agg(inst=("inst", "sum"), samples=("samples", "sum")).sort_values("inst", ascending=False)
+    g["pct_inst"] = (100 * g.inst / total).round(1)
+    g["pct_samples"] = (100 * g.samples / df["samples"].sum()).round(1)
+    print(g.head(top).to_string())
+    stall_cols = [c for c in df.columns if c.startswith("stall_") and "Not Issued" not in c]
+    stalls = pd.Series({c: num(c).sum() for c in stall_cols}).sort_values(ascending=False)
+    print((100 * stalls / stalls.sum()).round(1).head(8).to_string())
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 18)
