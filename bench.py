@@ -64,12 +64,15 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons through NVML; only samples taken while `active`
+    (the timed region) are reported."""
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = False
+        self.ready = threading.Event()
         self._stop_event = threading.Event()
 
     def run(self):
@@ -77,30 +80,33 @@ class ClockSampler(threading.Thread):
             import pynvml
 
             pynvml.nvmlInit()
-            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            # NVML enumerates physical GPUs: honour CUDA_VISIBLE_DEVICES when it lists indices
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in visible.split(",") if v.strip().isdigit()]
+            physical = int(ids[self.index]) if self.index < len(ids) else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
-            names = {
-                "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
-                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
-            }
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
             getter = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self._stop_event.is_set():
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                clock = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
                 mask = getter(handle)
-                for name, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.002)
+                self.ready.set()
+                if self.active:
+                    self.samples.append(clock)
+                    for name, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                time.sleep(0.0005)
         except Exception as exc:  # NVML missing: report it, never fail the bench
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._stop_event.set()
         self.join(timeout=2)
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         ordered = sorted(self.samples)
         return {"sm_mhz": ordered[len(ordered) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(ordered)}
 
@@ -259,10 +265,12 @@ def run_ours(args):
     # ---- device-timed steps (value) ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.ready.wait(timeout=10)
     launches_before = sum(_lib.LAUNCHES.values())
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    sampler.active = True
     for i in range(args.steps):
         flush.fill_(float(i))  # evict L2 (126 MB) between timed steps; outside the event pair
         if world > 1:
@@ -271,6 +279,7 @@ def run_ours(args):
         step()
         ends[i].record()
     barrier()
+    sampler.active = False
     gpu_launches = sum(_lib.LAUNCHES.values()) - launches_before
     times_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = sum(times_ms)

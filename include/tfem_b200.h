@@ -69,16 +69,19 @@ typedef struct tfem_bilinear {
  * A tile owns a set of CSR rows; its elements are all elements touching those rows. */
 typedef struct tfem_tile_plan {
   int64_t n_tiles;
-  const int32_t* tile_ptr;        /* [n_tiles+1,4] first vertex / element / row / run of each tile  */
-  const int32_t* tile_vert;       /* geometry vertex id (row of `coords`) of each tile-local vertex  */
-  const uint32_t* tile_elem;      /* tile-local connectivity, v0 | v1<<10 | v2<<20                    */
-  const int32_t* row_id;          /* global row (DOF) of each tile row                                 */
-  const int32_t* row_meta;        /* out_base | pos_diag<<16 : first slot of the row in the tile output*/
-  const int32_t* row_corner_ptr;  /* [n_rows+1] offsets into `corner`                                 */
-  const uint32_t* corner;         /* elem | k<<12 | posA<<16 | posB<<24 per (row, incident element)  */
-  const int32_t* run_start;       /* CSR offset of the first entry of each run of consecutive rows    */
-  const int32_t* run_meta;        /* out_base | len<<16 of each run                                    */
-  int32_t max_vert, max_elem, max_out, max_rows; /* per-tile maxima (shared-memory sizing)           */
+  const int32_t* tile_off; /* [n_tiles+1] word offset of each tile's blob inside `blob`; multiples of 4,
+                              so every blob is 16 B aligned and a whole number of 16 B units (TMA bulk copy) */
+  const int32_t* blob;     /* per tile, 32-bit words, every section padded to a multiple of 4 words:
+                                header[8]      n_vert, n_elem, n_rows, n_runs, n_corner, n_out, 0, 0
+                                vert[n_vert]   row of `coords` of each tile-local vertex
+                                elem[n_elem]   tile-local connectivity  v0 | v1<<10 | v2<<20
+                                row_id[n_rows] global row (DOF) of each owned row
+                                row_meta[n_rows]   out_base | pos_diag<<16  (slot of the row in the tile image)
+                                row_cptr[n_rows+1] offsets into corner[]
+                                corner[n_corner]   elem | k<<12 | posA<<16 | posB<<24 per (row, incident element)
+                                run_start[n_runs]  CSR offset of the first entry of a run of consecutive rows
+                                run_meta[n_runs]   out_base | len<<16                                           */
+  int32_t max_vert, max_elem, max_out, max_blob_words; /* per-tile maxima (shared-memory sizing) */
 } tfem_tile_plan;
 
 int tfem_abi_version(void);

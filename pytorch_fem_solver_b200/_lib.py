@@ -43,19 +43,12 @@ class TilePlan(Structure):
 
     _fields_ = [
         ("n_tiles", c_int64),
-        ("tile_ptr", c_void_p),
-        ("tile_vert", c_void_p),
-        ("tile_elem", c_void_p),
-        ("row_id", c_void_p),
-        ("row_meta", c_void_p),
-        ("row_corner_ptr", c_void_p),
-        ("corner", c_void_p),
-        ("run_start", c_void_p),
-        ("run_meta", c_void_p),
+        ("tile_off", c_void_p),
+        ("blob", c_void_p),
         ("max_vert", c_int32),
         ("max_elem", c_int32),
         ("max_out", c_int32),
-        ("max_rows", c_int32),
+        ("max_blob_words", c_int32),
     ]
 
 

@@ -160,36 +160,43 @@ def block_tiles(points: torch.Tensor, rows_per_tile: int):
 
 @dataclass
 class TilePlan:
-    """Device arrays of struct tfem_tile_plan plus bookkeeping."""
+    """Device arrays of struct tfem_tile_plan (one packed blob per tile) plus bookkeeping."""
 
     n_tiles: int
-    tile_ptr: torch.Tensor
-    tile_vert: torch.Tensor
-    tile_elem: torch.Tensor
-    row_id: torch.Tensor
-    row_meta: torch.Tensor
-    row_corner_ptr: torch.Tensor
-    corner: torch.Tensor
-    run_start: torch.Tensor
-    run_meta: torch.Tensor
+    tile_off: torch.Tensor  # (n_tiles+1,) int32 word offsets, multiples of 4
+    blob: torch.Tensor  # int32 words, layout in include/tfem_b200.h
     max_vert: int
     max_elem: int
     max_out: int
+    max_blob_words: int
     max_rows: int
     halo_factor: float  # tile elements / mesh elements (1.0 = every element computed once)
-    index_bytes: int  # bytes of plan arrays the kernel reads per launch
+    index_bytes: int  # bytes of plan data the kernel reads per launch
 
     def c_struct(self) -> "_lib.TilePlan":
         s = _lib.TilePlan()
         s.n_tiles = self.n_tiles
-        for name in ("tile_ptr", "tile_vert", "tile_elem", "row_id", "row_meta", "row_corner_ptr", "corner", "run_start", "run_meta"):
-            setattr(s, name, getattr(self, name).data_ptr())
-        s.max_vert, s.max_elem, s.max_out, s.max_rows = self.max_vert, self.max_elem, self.max_out, self.max_rows
+        s.tile_off = self.tile_off.data_ptr()
+        s.blob = self.blob.data_ptr()
+        s.max_vert, s.max_elem, s.max_out, s.max_blob_words = self.max_vert, self.max_elem, self.max_out, self.max_blob_words
         return s
 
     def to(self, device) -> "TilePlan":
         moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
         return TilePlan(**moved)
+
+    def sections(self, tile: int) -> dict:
+        """Decode one tile's blob into named integer arrays (tests / debugging)."""
+        off = self.tile_off.cpu().numpy().astype("int64")
+        words = self.blob[int(off[tile]) : int(off[tile + 1])].cpu().numpy().astype("int64") & 0xFFFFFFFF
+        n_vert, n_elem, n_rows, n_runs, n_corner, n_out = (int(w) for w in words[:6])
+        pad4 = lambda n: (n + 3) & ~3  # noqa: E731
+        out, pos = {"n_out": n_out}, 8
+        for name, n in (("vert", n_vert), ("elem", n_elem), ("row_id", n_rows), ("row_meta", n_rows),
+                        ("row_cptr", n_rows + 1), ("corner", n_corner), ("run_start", n_runs), ("run_meta", n_runs)):
+            out[name] = words[pos : pos + n]
+            pos += pad4(n)
+        return out
 
 
 def _ptr_from_sorted(group: torch.Tensor, n_groups: int) -> torch.Tensor:
@@ -303,32 +310,56 @@ def build_tile_plan(
     run_meta = out_base[run_first] | (run_len << 16)
     run_ptr = _ptr_from_sorted(row_tile[run_first], n_tiles)
 
-    tile_ptr = torch.stack([vert_ptr, elem_ptr, row_ptr, run_ptr], dim=1).to(torch.int32).contiguous()
-    as_i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731  (values < 2**31 by the checks above)
-    to_u32 = _wrap_u32
-    plan = TilePlan(
+    # 7. pack everything a tile needs into one 16 B aligned blob (a single TMA bulk copy per CTA)
+    def pad4(t):
+        return (t + 3) & ~3
+
+    tiles = torch.arange(n_tiles, device=device)
+    n_v, n_e, n_r, n_u = (p[1:] - p[:-1] for p in (vert_ptr, elem_ptr, row_ptr, run_ptr))
+    corner_base = row_corner_ptr[row_ptr[:-1]]
+    n_c = row_corner_ptr[row_ptr[1:]] - corner_base
+    sizes = [torch.full_like(n_v, 8), pad4(n_v), pad4(n_e), pad4(n_r), pad4(n_r), pad4(n_r + 1), pad4(n_c), pad4(n_u), pad4(n_u)]
+    tile_words = sum(sizes)
+    tile_off = torch.zeros(n_tiles + 1, dtype=torch.int64, device=device)
+    tile_off[1:] = torch.cumsum(tile_words, 0)
+    total_words = int(tile_off[-1].item())
+    if total_words >= 2**31:
+        raise ValueError("tile plan too large for 32-bit word offsets")
+    starts = [tile_off[:-1]]
+    for size in sizes[:-1]:
+        starts.append(starts[-1] + size)
+    s_hdr, s_vert, s_elem, s_rid, s_rmeta, s_rcptr, s_corner, s_rstart, s_rmeta2 = starts
+    blob = torch.zeros(total_words, dtype=torch.int64, device=device)
+    for k, field in enumerate((n_v, n_e, n_r, n_u, n_c, tile_out)):
+        blob[s_hdr + k] = field
+    blob[s_vert[vert_tile] + torch.arange(vert_tile.numel(), device=device) - vert_ptr[vert_tile]] = tile_vert
+    blob[s_elem[pair_tile] + torch.arange(pair_tile.numel(), device=device) - elem_ptr[pair_tile]] = tile_elem
+    row_local = torch.arange(n_dof, device=device) - row_ptr[row_tile]
+    blob[s_rid[row_tile] + row_local] = row_sorted
+    blob[s_rmeta[row_tile] + row_local] = row_meta
+    cptr_tile = torch.repeat_interleave(tiles, n_r + 1)
+    cptr_local = torch.arange(cptr_tile.numel(), device=device) - (row_ptr[:-1] + tiles)[cptr_tile]
+    blob[s_rcptr[cptr_tile] + cptr_local] = row_corner_ptr[row_ptr[cptr_tile] + cptr_local] - corner_base[cptr_tile]
+    blob[s_corner[c_tile] + torch.arange(c_tile.numel(), device=device) - corner_base[c_tile]] = corner
+    run_tile = row_tile[run_first]
+    run_local = torch.arange(run_tile.numel(), device=device) - run_ptr[run_tile]
+    blob[s_rstart[run_tile] + run_local] = run_start
+    blob[s_rmeta2[run_tile] + run_local] = run_meta
+
+    blob32 = _wrap_u32(blob)
+    tile_off32 = tile_off.to(torch.int32).contiguous()
+    return TilePlan(
         n_tiles=n_tiles,
-        tile_ptr=tile_ptr,
-        tile_vert=as_i32(tile_vert),
-        tile_elem=to_u32(tile_elem),
-        row_id=as_i32(row_sorted),
-        row_meta=as_i32(row_meta),
-        row_corner_ptr=as_i32(row_corner_ptr),
-        corner=to_u32(corner),
-        run_start=as_i32(run_start),
-        run_meta=to_u32(run_meta),
+        tile_off=tile_off32,
+        blob=blob32,
         max_vert=max_vert,
         max_elem=max_elem,
         max_out=max_out,
-        max_rows=int((row_ptr[1:] - row_ptr[:-1]).max().item()),
+        max_blob_words=int(tile_words.max().item()),
+        max_rows=int(n_r.max().item()),
         halo_factor=float(pair_keys.shape[0]) / max(n_el, 1),
-        index_bytes=0,
+        index_bytes=4 * (blob32.numel() + tile_off32.numel()),
     )
-    plan.index_bytes = sum(
-        getattr(plan, n).numel() * 4
-        for n in ("tile_ptr", "tile_vert", "tile_elem", "row_id", "row_meta", "row_corner_ptr", "corner", "run_start", "run_meta")
-    )
-    return plan
 
 
 def _wrap_u32(t: torch.Tensor) -> torch.Tensor:

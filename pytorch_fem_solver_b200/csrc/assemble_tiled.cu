@@ -5,136 +5,297 @@
 // (tests/test_assembly.py:68-84)  ->  (integrand*dx).sum(-3) (abstract_basis.py:83,104)  ->
 // index_put_(accumulate=True) (abstract_basis.py:87-91,106-110).
 //
-// A tile owns a set of CSR rows.  Its CTA
-//   A. stages the coordinates of every vertex the tile touches in shared memory,
-//   B. computes each tile element's local matrix (6 unique entries, the form is symmetric) and
-//      load (3 entries) ONCE, into shared memory (elements on a tile border are recomputed by the
-//      neighbouring tile: a halo of ~13% for 16x16 vertex blocks),
-//   C. lets one thread per owned row sum its incident-element contributions in increasing
-//      element order into a shared image of the row's CSR entries,
-//   D. streams the image to csr_val in runs of consecutive rows (coalesced 8 B stores).
-// HBM traffic per element is therefore ~coords + index plan + outputs; nothing is re-read.
+// A tile owns a set of CSR rows; all of its index data sits in ONE contiguous, 16 B aligned blob
+// that a single elected thread pulls into shared memory with a TMA bulk copy
+// (cp.async.bulk ... mbarrier::complete_tx) while the other threads wait on the mbarrier.  Then
+//   A. every tile vertex is gathered once: coordinates (one 16 B load) and, for the sin*sin
+//      source, sin/cos of (w x, w y) -> shared;
+//   B. every tile element is integrated ONCE: 6 unique matrix entries (the form is symmetric)
+//      and 3 load entries -> shared.  f at the quadrature points comes from the vertex-0
+//      sin/cos and a short Taylor rotation by the (tiny) in-element phase, so no fp64 sin() runs
+//      per quadrature point.  Elements on a tile border are recomputed by the neighbouring tile
+//      (halo ~14-20%);
+//   C. one thread per owned row sums its incident-element contributions in increasing element
+//      order into a shared image of the row's CSR entries (no atomics: bitwise reproducible);
+//   D. the image is streamed to csr_val in runs of consecutive rows (coalesced 8 B stores).
+// HBM traffic is therefore coords + index blob + outputs, each touched once.
 #include "common.cuh"
 
 namespace tfem {
 
-template <typename T>
-struct PlanDev {
-  const int32_t* tile_ptr;
-  const int32_t* tile_vert;
-  const uint32_t* tile_elem;
-  const int32_t* row_id;
-  const int32_t* row_meta;
-  const int32_t* row_corner_ptr;
-  const uint32_t* corner;
-  const int32_t* run_start;
-  const int32_t* run_meta;
-  int max_vert, max_elem, max_out;
-};
+// ---- mbarrier / TMA bulk-copy wrappers (PTX ISA 8.x, sm_90+) --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <typename T, int THREADS, bool HAS_MAT, bool HAS_LOAD>
-__global__ void __launch_bounds__(THREADS) assemble_tiled_kernel(const PlanDev<T> plan,
-                                                                 const T* __restrict__ coords,
-                                                                 const QuadT<T> quad, const T alpha,
-                                                                 const T beta, const SourceT<T> src,
-                                                                 T* __restrict__ csr_val,
-                                                                 T* __restrict__ load) {
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+constexpr int kBlobHeader = 8;
+
+template <int ORDER> struct NQ;
+template <> struct NQ<1> { static constexpr int value = 1; };
+template <> struct NQ<2> { static constexpr int value = 3; };
+template <> struct NQ<3> { static constexpr int value = 4; };
+template <> struct NQ<4> { static constexpr int value = 6; };
+
+__device__ __forceinline__ void sincos_full(double x, double& s, double& c) { sincos(x, &s, &c); }
+__device__ __forceinline__ void sincos_full(float x, float& s, float& c) { sincosf(x, &s, &c); }
+
+// |phase| below which the 7th/6th-order Taylor rotation is exact to < 1e-18 relative
+template <typename T> __device__ __forceinline__ T small_phase_limit() { return T(0.02); }
+
+// sin(t), cos(t) for |t| <= 0.02
+template <typename T>
+__device__ __forceinline__ void sincos_small(T t, T& s, T& c) {
+  const T z = t * t;
+  T ps = fma(z, T(-1.0 / 5040.0), T(1.0 / 120.0));
+  ps = fma(z, ps, T(-1.0 / 6.0));
+  s = fma(t * z, ps, t);
+  T pc = fma(z, T(-1.0 / 720.0), T(1.0 / 24.0));
+  pc = fma(z, pc, T(-0.5));
+  c = fma(z, pc, T(1));
+}
+
+template <typename T, int THREADS, int ORDER, int SRC, bool HAS_MAT>
+__global__ void __launch_bounds__(THREADS) assemble_tiled_kernel(
+    const int32_t* __restrict__ tile_off, const int32_t* __restrict__ blob, const int max_vert,
+    const int elem_stride, const int max_blob_words, const T* __restrict__ coords, const QuadT<T> quad,
+    const T alpha, const T beta, const SourceT<T> src, T* __restrict__ csr_val, T* __restrict__ load) {
+  constexpr int NQV = NQ<ORDER>::value;
+  constexpr bool HAS_LOAD = SRC != TFEM_SRC_NONE;
+  constexpr bool SINSIN = SRC == TFEM_SRC_SINSIN;
+  constexpr int VFIELDS = SINSIN ? 6 : 2;
+
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sx = reinterpret_cast<T*>(smem_raw);
-  T* sy = sx + plan.max_vert;
-  T* sloc = sy + plan.max_vert;           // [9][max_elem]: K00 K11 K22 K01 K12 K20 b0 b1 b2
-  T* sout = sloc + 9 * plan.max_elem;     // [max_out] image of the tile's CSR entries
+  // [ mbarrier (16 B) | blob (16 B aligned, whole 16 B units) | vertex fields | sloc[9][elem_stride] | sout ]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  int32_t* sblob = reinterpret_cast<int32_t*>(smem_raw + 16);
+  T* vtx = reinterpret_cast<T*>(sblob + max_blob_words);
+  T* sloc = vtx + VFIELDS * max_vert;
+  T* sout = sloc + 9 * elem_stride;
+
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
-  const int4 p0 = __ldg(reinterpret_cast<const int4*>(plan.tile_ptr) + tile);
-  const int4 p1 = __ldg(reinterpret_cast<const int4*>(plan.tile_ptr) + tile + 1);
-  const int n_vert = p1.x - p0.x, n_elem = p1.y - p0.y, n_rows = p1.z - p0.z, n_runs = p1.w - p0.w;
-  const int max_elem = plan.max_elem;
+  const int off0 = __ldg(tile_off + tile);
+  const int words = __ldg(tile_off + tile + 1) - off0;
 
-  // ---- A: coordinates of the tile's vertices -> shared --------------------------------------
-  for (int i = tid; i < n_vert; i += THREADS) {
-    const int v = __ldg(plan.tile_vert + p0.x + i);
-    T x, y;
-    load_xy(coords, v, x, y);
-    sx[i] = x;
-    sy[i] = y;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(bar, (uint32_t)words * 4u);
+    bulk_g2s(sblob, blob + off0, (uint32_t)words * 4u, bar);
   }
-  if (HAS_MAT) {
-    // runs tile the image in order, so the last run ends it
-    const int last = n_runs > 0 ? __ldg(plan.run_meta + p1.w - 1) : 0;
-    const int n_out = (last & 0xffff) + ((last >> 16) & 0xffff);
+  __syncthreads();  // barrier object initialised and visible to every waiter
+  mbar_wait(bar, 0);
+
+  const int n_vert = sblob[0], n_elem = sblob[1], n_rows = sblob[2], n_runs = sblob[3], n_corner = sblob[4],
+            n_out = sblob[5];
+  const int32_t* s_vert = sblob + kBlobHeader;
+  const uint32_t* s_elem = reinterpret_cast<const uint32_t*>(s_vert + pad4(n_vert));
+  const int32_t* s_row_id = reinterpret_cast<const int32_t*>(s_elem + pad4(n_elem));
+  const int32_t* s_row_meta = s_row_id + pad4(n_rows);
+  const int32_t* s_row_cptr = s_row_meta + pad4(n_rows);
+  const uint32_t* s_corner = reinterpret_cast<const uint32_t*>(s_row_cptr + pad4(n_rows + 1));
+  const int32_t* s_run_start = reinterpret_cast<const int32_t*>(s_corner + pad4(n_corner));
+  const int32_t* s_run_meta = s_run_start + pad4(n_runs);
+
+  // ---- A: tile vertices -> shared -------------------------------------------------------------
+  T* vx = vtx;
+  T* vy = vtx + max_vert;
+  for (int i = tid; i < n_vert; i += THREADS) {
+    T x, y;
+    load_xy(coords, s_vert[i], x, y);
+    vx[i] = x;
+    vy[i] = y;
+    if constexpr (SINSIN) {
+      T s, c;
+      sincos_full(src.p1 * x, s, c);
+      vtx[2 * max_vert + i] = s;
+      vtx[3 * max_vert + i] = c;
+      sincos_full(src.p2 * y, s, c);
+      vtx[4 * max_vert + i] = s;
+      vtx[5 * max_vert + i] = c;
+    }
+  }
+  if constexpr (HAS_MAT) {
     for (int i = tid; i < n_out; i += THREADS) sout[i] = T(0);
   }
   __syncthreads();
 
-  // ---- B: local matrices and loads, one element per thread ----------------------------------
+  // ---- B: local matrices and loads, each tile element once ------------------------------------
   for (int el = tid; el < n_elem; el += THREADS) {
-    const uint32_t packed = __ldg(plan.tile_elem + p0.y + el);
+    const uint32_t packed = s_elem[el];
     const int a = packed & 1023u, b = (packed >> 10) & 1023u, c = (packed >> 20) & 1023u;
-    const T x0 = sx[a], y0 = sy[a], x1 = sx[b], y1 = sy[b], x2 = sx[c], y2 = sy[c];
-    const TriGeom<T> g = tri_geom(x0, y0, x1, y1, x2, y2);
-    if (HAS_MAT) {
-      const T g0x = -g.i00 - g.i10, g0y = -g.i01 - g.i11;
-      const T g1x = g.i00, g1y = g.i01, g2x = g.i10, g2y = g.i11;
-      const T ka = alpha * (quad.wsum * g.det);
-      const T mb = beta * g.det;
-      sloc[0 * max_elem + el] = ka * (g0x * g0x + g0y * g0y) + mb * quad.mref[0];
-      sloc[1 * max_elem + el] = ka * (g1x * g1x + g1y * g1y) + mb * quad.mref[4];
-      sloc[2 * max_elem + el] = ka * (g2x * g2x + g2y * g2y) + mb * quad.mref[8];
-      sloc[3 * max_elem + el] = ka * (g0x * g1x + g0y * g1y) + mb * quad.mref[1];
-      sloc[4 * max_elem + el] = ka * (g1x * g2x + g1y * g2y) + mb * quad.mref[5];
-      sloc[5 * max_elem + el] = ka * (g2x * g0x + g2y * g0y) + mb * quad.mref[6];
+    const T x0 = vx[a], y0 = vy[a];
+    const T ax = vx[b] - x0, ay = vy[b] - y0;  // J = [[ax, bx], [ay, by]] (basis.py:87-88)
+    const T bx = vx[c] - x0, by = vy[c] - y0;
+    const T det = ax * by - bx * ay;  // signed (element_tri.py:139)
+    if constexpr (HAS_MAT) {
+      const T r = T(1) / det;
+      const T g1x = r * by, g1y = -(r * bx);  // rows of J^-1 = grad(phi_1), grad(phi_2)
+      const T g2x = -(r * ay), g2y = r * ax;
+      const T g0x = -g1x - g2x, g0y = -g1y - g2y;
+      const T ka = alpha * (quad.wsum * det);
+      const T mb = beta * det;
+      sloc[0 * elem_stride + el] = fma(ka, g0x * g0x + g0y * g0y, mb * quad.mref[0]);
+      sloc[1 * elem_stride + el] = fma(ka, g1x * g1x + g1y * g1y, mb * quad.mref[4]);
+      sloc[2 * elem_stride + el] = fma(ka, g2x * g2x + g2y * g2y, mb * quad.mref[8]);
+      sloc[3 * elem_stride + el] = fma(ka, g0x * g1x + g0y * g1y, mb * quad.mref[1]);
+      sloc[4 * elem_stride + el] = fma(ka, g1x * g2x + g1y * g2y, mb * quad.mref[5]);
+      sloc[5 * elem_stride + el] = fma(ka, g2x * g0x + g2y * g0y, mb * quad.mref[6]);
     }
-    if (HAS_LOAD) {
+    if constexpr (HAS_LOAD) {
       T b0 = T(0), b1 = T(0), b2 = T(0);
-      for (int q = 0; q < quad.n_q; ++q) {
-        const T px = quad.l0[q] * x0 + quad.l1[q] * x1 + quad.l2[q] * x2;
-        const T py = quad.l0[q] * y0 + quad.l1[q] * y1 + quad.l2[q] * y2;
-        const T wf = (quad.w[q] * g.det) * source_eval(src, px, py);
-        b0 += wf * quad.l0[q];
-        b1 += wf * quad.l1[q];
-        b2 += wf * quad.l2[q];
+      if constexpr (SINSIN) {
+        // phase of the source relative to vertex 0: w*(x_q - x0) = xi*(w ax) + eta*(w bx)
+        const T uax = src.p1 * ax, ubx = src.p1 * bx, uay = src.p2 * ay, uby = src.p2 * by;
+        const T lim = small_phase_limit<T>();
+        const bool small = fabs(uax) < lim && fabs(ubx) < lim && fabs(uay) < lim && fabs(uby) < lim;
+        const T sx0 = vtx[2 * max_vert + a], cx0 = vtx[3 * max_vert + a];
+        const T sy0 = vtx[4 * max_vert + a], cy0 = vtx[5 * max_vert + a];
+        const T amp = src.p0 * det;
+#pragma unroll
+        for (int q = 0; q < NQV; ++q) {
+          T sx, sy;
+          if (small) {
+            T s, cth;
+            sincos_small(fma(quad.l1[q], uax, quad.l2[q] * ubx), s, cth);
+            sx = fma(sx0, cth, cx0 * s);  // sin(w x0 + theta)
+            sincos_small(fma(quad.l1[q], uay, quad.l2[q] * uby), s, cth);
+            sy = fma(sy0, cth, cy0 * s);
+          } else {  // coarse element: evaluate the source directly
+            sx = sin(src.p1 * fma(quad.l1[q], ax, fma(quad.l2[q], bx, x0)));
+            sy = sin(src.p2 * fma(quad.l1[q], ay, fma(quad.l2[q], by, y0)));
+          }
+          const T wf = (quad.w[q] * amp) * (sx * sy);
+          b0 = fma(wf, quad.l0[q], b0);
+          b1 = fma(wf, quad.l1[q], b1);
+          b2 = fma(wf, quad.l2[q], b2);
+        }
+      } else {  // constant source: sum_q w_q l_k(q) is a per-order constant
+        const T wf = src.p0 * det;
+#pragma unroll
+        for (int q = 0; q < NQV; ++q) {
+          b0 = fma(wf * quad.w[q], quad.l0[q], b0);
+          b1 = fma(wf * quad.w[q], quad.l1[q], b1);
+          b2 = fma(wf * quad.w[q], quad.l2[q], b2);
+        }
       }
-      sloc[6 * max_elem + el] = b0;
-      sloc[7 * max_elem + el] = b1;
-      sloc[8 * max_elem + el] = b2;
+      sloc[6 * elem_stride + el] = b0;
+      sloc[7 * elem_stride + el] = b1;
+      sloc[8 * elem_stride + el] = b2;
     }
   }
   __syncthreads();
 
   // ---- C: one thread per owned row gathers its corners in increasing element order ----------
   for (int j = tid; j < n_rows; j += THREADS) {
-    const int meta = __ldg(plan.row_meta + p0.z + j);
+    const int meta = s_row_meta[j];
     const int base = meta & 0xffff, pos_diag = (meta >> 16) & 0xff;
-    const int c0 = __ldg(plan.row_corner_ptr + p0.z + j);
-    const int c1 = __ldg(plan.row_corner_ptr + p0.z + j + 1);
+    const int c0 = s_row_cptr[j], c1 = s_row_cptr[j + 1];
     T diag = T(0), rhs = T(0);
-    for (int c = c0; c < c1; ++c) {
-      const uint32_t cw = __ldg(plan.corner + c);
+    for (int cidx = c0; cidx < c1; ++cidx) {
+      const uint32_t cw = s_corner[cidx];
       const int el = cw & 0xfffu, k = (cw >> 12) & 3u;
-      if (HAS_MAT) {
+      if constexpr (HAS_MAT) {
         const int pa = (cw >> 16) & 0xffu, pb = cw >> 24;
         const int kb = k == 0 ? 2 : k - 1;  // (k+2) % 3
-        diag += sloc[k * max_elem + el];
-        sout[base + pa] += sloc[(3 + k) * max_elem + el];   // entry (k+1, k)
-        sout[base + pb] += sloc[(3 + kb) * max_elem + el];  // entry (k+2, k)
+        diag += sloc[k * elem_stride + el];
+        sout[base + pa] += sloc[(3 + k) * elem_stride + el];   // entry (k+1, k)
+        sout[base + pb] += sloc[(3 + kb) * elem_stride + el];  // entry (k+2, k)
       }
-      if (HAS_LOAD) rhs += sloc[(6 + k) * max_elem + el];
+      if constexpr (HAS_LOAD) rhs += sloc[(6 + k) * elem_stride + el];
     }
-    if (HAS_MAT) sout[base + pos_diag] += diag;
-    if (HAS_LOAD) load[__ldg(plan.row_id + p0.z + j)] = rhs;
+    if constexpr (HAS_MAT) {
+      if (c1 > c0) sout[base + pos_diag] += diag;
+    }
+    if constexpr (HAS_LOAD) load[s_row_id[j]] = rhs;
   }
 
   // ---- D: stream the row images out, one warp per run of consecutive rows --------------------
-  if (HAS_MAT) {
+  if constexpr (HAS_MAT) {
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
     for (int r = warp; r < n_runs; r += THREADS / 32) {
-      const int gstart = __ldg(plan.run_start + p0.w + r);
-      const int meta = __ldg(plan.run_meta + p0.w + r);
+      const int gstart = s_run_start[r];
+      const int meta = s_run_meta[r];
       const int base = meta & 0xffff, len = (meta >> 16) & 0xffff;
       for (int i = lane; i < len; i += 32) csr_val[(int64_t)gstart + i] = sout[base + i];
     }
+  }
+}
+
+template <typename T>
+size_t tiled_smem_bytes(const tfem_tile_plan* hp, int src_kind, int* elem_stride) {
+  const int vfields = src_kind == TFEM_SRC_SINSIN ? 6 : 2;
+  *elem_stride = (hp->max_elem + 31) & ~31;
+  return 16 + 4 * (size_t)((hp->max_blob_words + 3) & ~3) +
+         sizeof(T) * ((size_t)vfields * hp->max_vert + (size_t)9 * *elem_stride + (size_t)hp->max_out);
+}
+
+template <typename T, int THREADS, int ORDER, int SRC, bool HAS_MAT>
+int launch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad, T alpha, T beta,
+                 const SourceT<T>& src, T* csr_val, T* load, cudaStream_t s) {
+  int elem_stride = 0;
+  const size_t smem = tiled_smem_bytes<T>(hp, SRC, &elem_stride);
+  if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
+  auto kern = assemble_tiled_kernel<T, THREADS, ORDER, SRC, HAS_MAT>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return TFEM_ERR_LAUNCH;
+  kern<<<(unsigned)hp->n_tiles, THREADS, smem, s>>>(hp->tile_off, hp->blob, hp->max_vert, elem_stride, (hp->max_blob_words + 3) & ~3,
+                                                    coords, quad, alpha, beta, src, csr_val, load);
+  return check_launch();
+}
+
+template <typename T, int THREADS, int ORDER>
+int dispatch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad, T alpha, T beta,
+                   const SourceT<T>& src, T* csr_val, T* load, cudaStream_t s) {
+  const int kind = load ? src.kind : TFEM_SRC_NONE;
+  if (csr_val) {
+    if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, THREADS, ORDER, TFEM_SRC_SINSIN, true>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+    if (kind == TFEM_SRC_CONST) return launch_tiled<T, THREADS, ORDER, TFEM_SRC_CONST, true>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+    return launch_tiled<T, THREADS, ORDER, TFEM_SRC_NONE, true>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+  }
+  if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, THREADS, ORDER, TFEM_SRC_SINSIN, false>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+  if (kind == TFEM_SRC_CONST) return launch_tiled<T, THREADS, ORDER, TFEM_SRC_CONST, false>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+  return TFEM_ERR_BAD_ARG;
+}
+
+template <typename T>
+int assemble_tiled_impl_zero(const tfem_tile_plan* hp, const T* coords, int quad_order, const tfem_bilinear* form,
+                             const SourceT<T>& src, T* csr_val, T* load, void* stream) {
+  const QuadT<T> quad = make_quad<T>(quad_order);
+  const T alpha = form ? T(form->alpha) : T(0), beta = form ? T(form->beta) : T(0);
+  auto s = static_cast<cudaStream_t>(stream);
+  constexpr int THREADS = 256;
+  switch (quad_order) {
+    case 1: return dispatch_tiled<T, THREADS, 1>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+    case 2: return dispatch_tiled<T, THREADS, 2>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+    case 3: return dispatch_tiled<T, THREADS, 3>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+    default: return dispatch_tiled<T, THREADS, 4>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
   }
 }
 
@@ -145,39 +306,21 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   if (hp->n_tiles == 0) return TFEM_OK;
   if (!coords || (!csr_val && !load)) return TFEM_ERR_BAD_ARG;
   if (csr_val && !form) return TFEM_ERR_BAD_ARG;
-  if (!hp->tile_ptr || !hp->tile_vert || !hp->tile_elem || !hp->row_id || !hp->row_meta ||
-      !hp->row_corner_ptr || !hp->corner || !hp->run_start || !hp->run_meta)
-    return TFEM_ERR_BAD_ARG;
+  if (!hp->tile_off || !hp->blob) return TFEM_ERR_BAD_ARG;
   if (hp->max_vert > 1024 || hp->max_elem > 4096 || hp->max_out > 65535) return TFEM_ERR_TOO_LARGE;
   if (hp->n_tiles > kMaxIndex) return TFEM_ERR_TOO_LARGE;
   if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
   const SourceT<T> src = make_source<T>(source);
   if (load && (src.kind == TFEM_SRC_SAMPLED || src.kind < TFEM_SRC_NONE || src.kind > TFEM_SRC_SINSIN))
     return TFEM_ERR_BAD_ARG;  // sampled sources go through tfem_tri_p1_local_forms
-  const QuadT<T> quad = make_quad<T>(quad_order);
-  const PlanDev<T> plan{hp->tile_ptr, hp->tile_vert, hp->tile_elem, hp->row_id, hp->row_meta,
-                        hp->row_corner_ptr, hp->corner, hp->run_start, hp->run_meta,
-                        hp->max_vert, hp->max_elem, hp->max_out};
-  const size_t smem = sizeof(T) * ((size_t)2 * hp->max_vert + (size_t)9 * hp->max_elem + (size_t)hp->max_out);
-  if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
-  const T alpha = form ? T(form->alpha) : T(0), beta = form ? T(form->beta) : T(0);
-  constexpr int THREADS = 256;
-  auto s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)hp->n_tiles;
-#define TFEM_LAUNCH_TILED(MAT, LOAD)                                                              \
-  do {                                                                                            \
-    auto kern = assemble_tiled_kernel<T, THREADS, MAT, LOAD>;                                     \
-    if (smem > 48 * 1024 &&                                                                       \
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=     \
-            cudaSuccess)                                                                          \
-      return TFEM_ERR_LAUNCH;                                                                     \
-    kern<<<grid, THREADS, smem, s>>>(plan, coords, quad, alpha, beta, src, csr_val, load);        \
-  } while (0)
-  if (csr_val && load) TFEM_LAUNCH_TILED(true, true);
-  else if (csr_val) TFEM_LAUNCH_TILED(true, false);
-  else TFEM_LAUNCH_TILED(false, true);
-#undef TFEM_LAUNCH_TILED
-  return check_launch();
+  if (load && src.kind == TFEM_SRC_NONE) {
+    // f == 0: the load vector is zero; still produced by the kernel so every row is written
+    SourceT<T> zero = src;
+    zero.kind = TFEM_SRC_CONST;
+    zero.p0 = T(0);
+    return assemble_tiled_impl_zero(hp, coords, quad_order, form, zero, csr_val, load, stream);
+  }
+  return assemble_tiled_impl_zero(hp, coords, quad_order, form, src, csr_val, load, stream);
 }
 
 }  // namespace tfem

@@ -144,8 +144,7 @@ def assemble_csr_tiled(plan_struct, coords, quad_order, alpha, beta, source_kind
     lvec = fo.quad_reduce(fo.form_load(geo, f), geo["dx"]).reshape(n, 3)
     offsets = (np.arange(n) // lay.n_el_per_mesh) * lay.n_vert_per_mesh
     geom_conn = _np(lay.conn).astype(np.int64) + offsets[:, None]
-    nnz = csr_val.shape[0] if csr_val is not None else int(plan.run_start.max()) + 65536
-    n_dof = load.shape[0] if load is not None else int(plan.row_id.max()) + 1
+    nnz, n_dof = assemble_csr_tiled.current_sizes
     vals, vec = emulate_tiled(plan, None, local, lvec, geom_conn, nnz, n_dof)
     if csr_val is not None:
         csr_val.copy_(torch.from_numpy(vals))
@@ -228,6 +227,7 @@ def install(monkeypatch):
         plan = original(self, *args, **kwargs)
         assemble_csr_tiled.current_plan = plan
         assemble_csr_tiled.current_layout = self._layout
+        assemble_csr_tiled.current_sizes = (self.pattern.nnz, self.pattern.n_dof)
         return plan
 
     monkeypatch.setattr(abstract_basis.AbstractBasis, "tile_plan", tile_plan)

@@ -61,4 +61,5 @@ def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
     np.testing.assert_allclose(vals, ref_vals, rtol=1e-13, atol=1e-15)
     np.testing.assert_allclose(load, ref_load, rtol=1e-13, atol=1e-15)
     # every row is owned by exactly one tile
-    assert sorted(plan.row_id.tolist()) == list(range(n_dof))
+    owned = np.concatenate([plan.sections(t)["row_id"] for t in range(plan.n_tiles)])
+    assert sorted(owned.tolist()) == list(range(n_dof))
