@@ -72,7 +72,10 @@ typedef struct tfem_tile_plan {
   const int32_t* tile_off; /* [n_tiles+1] word offset of each tile's blob inside `blob`; multiples of 4,
                               so every blob is 16 B aligned and a whole number of 16 B units (TMA bulk copy) */
   const int32_t* blob;     /* per tile, 32-bit words, every section padded to a multiple of 4 words:
-                                header[8]      n_vert, n_elem, n_rows, n_runs, n_corner, n_out, 0, 0
+                                header[8]      n_vert, n_elem, n_rows, n_runs, n_corner, n_out, base_vertex, 0
+                                               (base_vertex: row of `coords` of a vertex near the middle of the
+                                               tile; the source's sin/cos are evaluated once there and rotated
+                                               to the other vertices)
                                 vert[n_vert]   row of `coords` of each tile-local vertex
                                 elem[n_elem]   tile-local connectivity  v0 | v1<<10 | v2<<20
                                 row_id[n_rows] global row (DOF) of each owned row

@@ -210,7 +210,7 @@ def build_tile_plan(
     dof_conn: torch.Tensor,
     pattern: CsrPattern,
     row_points: torch.Tensor | None = None,
-    rows_per_tile: int = 256,
+    rows_per_tile: int = 216,
     ordering: str = "block",
 ) -> TilePlan:
     """Partition CSR rows into tiles and precompute everything the fused kernel gathers.
@@ -330,7 +330,10 @@ def build_tile_plan(
         starts.append(starts[-1] + size)
     s_hdr, s_vert, s_elem, s_rid, s_rmeta, s_rcptr, s_corner, s_rstart, s_rmeta2 = starts
     blob = torch.zeros(total_words, dtype=torch.int64, device=device)
-    for k, field in enumerate((n_v, n_e, n_r, n_u, n_c, tile_out)):
+    # a vertex from the middle of each tile's (sorted) vertex list; tiles without elements get vertex 0
+    middle = (vert_ptr[:-1] + torch.div(n_v, 2, rounding_mode="floor")).clamp_max(max(tile_vert.numel() - 1, 0))
+    tile_base = torch.where(n_v > 0, tile_vert[middle] if tile_vert.numel() else torch.zeros_like(n_v), torch.zeros_like(n_v))
+    for k, field in enumerate((n_v, n_e, n_r, n_u, n_c, tile_out, tile_base)):
         blob[s_hdr + k] = field
     blob[s_vert[vert_tile] + torch.arange(vert_tile.numel(), device=device) - vert_ptr[vert_tile]] = tile_vert
     blob[s_elem[pair_tile] + torch.arange(pair_tile.numel(), device=device) - elem_ptr[pair_tile]] = tile_elem

@@ -29,3 +29,23 @@ def main(path, top=18):
 
 if __name__ == "__main__":
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 18)
+
+
+def segments(path):
+    """Instruction / sample totals between consecutive BAR.SYNC / SYNCS (phase boundaries), in address order."""
+    lines = open(path).read().split("\n")
+    df = pd.read_csv(io.StringIO("\n".join(lines[1:])), dtype=str)
+    inst = pd.to_numeric(df["Instructions Executed"], errors="coerce").fillna(0)
+    samp = pd.to_numeric(df["# Samples"], errors="coerce").fillna(0)
+    src = df["Source"].str.strip()
+    seg, acc_i, acc_s, n, fp = 0, 0.0, 0.0, 0, 0.0
+    for s, i, k in zip(src, inst, samp):
+        acc_i += i
+        acc_s += k
+        n += 1
+        if any(op in s for op in ("DFMA", "DMUL", "DADD")):
+            fp += i
+        if "BAR.SYNC" in s or "SYNCS.PHASECHK" in s:
+            print(f"segment {seg}: {n:5d} SASS lines  {acc_i/1e6:8.2f} M warp-instr ({100*fp/max(acc_i,1):4.1f}% fp64)  {acc_s:7.0f} samples   ends at: {s[:50]}")
+            seg, acc_i, acc_s, n, fp = seg + 1, 0.0, 0.0, 0, 0.0
+    print(f"segment {seg}: {n:5d} SASS lines  {acc_i/1e6:8.2f} M warp-instr ({100*fp/max(acc_i,1):4.1f}% fp64)  {acc_s:7.0f} samples   (tail)")
