@@ -228,20 +228,30 @@ def build_tile_plan(
     n_gv = int(gconn.max().item()) + 1 if n_el else 1
     crow = pattern.crow.long()
 
-    # 1. rows -> tiles
-    tile_of_row = None
-    if row_points is not None and ordering == "block":
-        tile_of_row, n_tiles, largest = block_tiles(row_points, rows_per_tile)
+    # 1. rows -> tiles.  Only rows some element touches are clustered; rows without elements
+    #    (isolated vertices, ghost columns of a multi-GPU owner) carry no work and are dealt out
+    #    evenly afterwards so that their (zero) load entry is still written.
+    active = torch.zeros(n_dof, dtype=torch.bool, device=device)
+    active[dconn.reshape(-1)] = True
+    active_rows = torch.nonzero(active, as_tuple=True)[0]
+    n_active = int(active_rows.numel())
+    tile_of_active = None
+    if row_points is not None and ordering == "block" and n_active:
+        tile_of_active, n_tiles, largest = block_tiles(row_points[active_rows], rows_per_tile)
         if largest > 2 * rows_per_tile:  # strongly graded mesh: fall back to balanced Z-order chunks
-            tile_of_row = None
-    if tile_of_row is None:
-        if row_points is not None and ordering != "natural":
-            order = morton_order(row_points)
+            tile_of_active = None
+    if tile_of_active is None:
+        if row_points is not None and ordering != "natural" and n_active:
+            order = morton_order(row_points[active_rows])
         else:
-            order = torch.arange(n_dof, device=device)
-        tile_of_row = torch.empty(n_dof, dtype=torch.int64, device=device)
-        tile_of_row[order] = torch.arange(n_dof, device=device) // rows_per_tile
-        n_tiles = (n_dof + rows_per_tile - 1) // rows_per_tile
+            order = torch.arange(n_active, device=device)
+        tile_of_active = torch.empty(n_active, dtype=torch.int64, device=device)
+        tile_of_active[order] = torch.arange(n_active, device=device) // rows_per_tile
+        n_tiles = max((n_active + rows_per_tile - 1) // rows_per_tile, 1)
+    tile_of_row = torch.empty(n_dof, dtype=torch.int64, device=device)
+    tile_of_row[active_rows] = tile_of_active
+    idle_rows = torch.nonzero(~active, as_tuple=True)[0]
+    tile_of_row[idle_rows] = torch.arange(idle_rows.numel(), device=device) % n_tiles
 
     # 2. (tile, element) incidences, tile-major / element ascending
     t_of_corner = tile_of_row[dconn]  # (N,3)
