@@ -65,26 +65,47 @@ typedef struct tfem_bilinear {
 } tfem_bilinear;
 
 /* Tile plan of the fused assembly kernel (all pointers DEVICE memory, built once per mesh by
- * pytorch_fem_solver_b200/csr.py; layouts documented in DESIGN.md "tile plan").
- * A tile owns a set of CSR rows; its elements are all elements touching those rows. */
+ * pytorch_fem_solver_b200/tileplan.py; see DESIGN.md "tile plan").
+ * A tile owns a set of CSR rows; its elements are all elements touching those rows.  Per tile there
+ * are two blobs of 32-bit words, each 16 B aligned and a whole number of 16 B units so that one TMA
+ * bulk copy fetches it; every section is padded to a multiple of 4 words; 16- and 8-bit sections
+ * are packed little-endian.
+ *
+ *   E blob ("early": producer warp + integration phase)
+ *     header[12]       n_vert, n_elem, n_rows, n_runs, n_out, n_contrib, base_vertex, n_lcontrib,
+ *                      n_heavy, 0, 0, 0
+ *                      (base_vertex: row of `coords` of a vertex near the middle of the tile; the
+ *                      source's sin/cos are evaluated once there and rotated to the other vertices)
+ *     vert[n_vert]     u32  row of `coords` of each tile-local vertex
+ *     elem[n_elem]     u32  tile-local connectivity  v0 | v1<<10 | v2<<20
+ *   L blob ("late": reduction phase)
+ *     row_id[n_rows]       u32  global row (DOF) of each owned row, ascending
+ *     run_start[n_runs]    u32  CSR offset of the first entry of a run of consecutive rows
+ *     run_meta[n_runs]     u32  image offset of the run | length<<16
+ *     ent_seg[n_out+1]     u16  offsets into contrib[] of each CSR entry of the tile; entries are
+ *                               numbered run after run ("image order"), so entry o of run r sits at
+ *                               csr_val[run_start[r] + o - image offset of r]
+ *     contrib[n_contrib]   u16  slot*elem_stride + tile element, slot 0..5 = K00 K11 K22 K01 K12 K20:
+ *                               a direct index into the CTA's local-matrix table; the contributions of
+ *                               an entry are listed in increasing element id, the summation order of
+ *                               the reference's index_put_/coalesce
+ *     lrow_seg[n_rows+1]   u16  offsets into lcontrib[] of each owned row
+ *     lcontrib[n_lcontrib] u16  k*elem_stride + tile element (k = local vertex): diagonal term of the
+ *                               row; its load term sits 6*elem_stride further
+ *     row_diag[n_rows]     u32  csr_val position of the row's diagonal when the row's thread sums it
+ *                               (same element list as the load entry), else 0xFFFFFFFF
+ *     heavy[n_heavy]       u16  image slots of the other entries with more than two contributions
+ *     heavy_pos[n_heavy]   u32  their csr_val positions
+ *   Entries with at most two contributions are summed by one thread per entry without a loop.     */
 typedef struct tfem_tile_plan {
   int64_t n_tiles;
-  const int32_t* tile_off; /* [n_tiles+1] word offset of each tile's blob inside `blob`; multiples of 4,
-                              so every blob is 16 B aligned and a whole number of 16 B units (TMA bulk copy) */
-  const int32_t* blob;     /* per tile, 32-bit words, every section padded to a multiple of 4 words:
-                                header[8]      n_vert, n_elem, n_rows, n_runs, n_corner, n_out, base_vertex, 0
-                                               (base_vertex: row of `coords` of a vertex near the middle of the
-                                               tile; the source's sin/cos are evaluated once there and rotated
-                                               to the other vertices)
-                                vert[n_vert]   row of `coords` of each tile-local vertex
-                                elem[n_elem]   tile-local connectivity  v0 | v1<<10 | v2<<20
-                                row_id[n_rows] global row (DOF) of each owned row
-                                row_meta[n_rows]   out_base | pos_diag<<16  (slot of the row in the tile image)
-                                row_cptr[n_rows+1] offsets into corner[]
-                                corner[n_corner]   elem | k<<12 | posA<<16 | posB<<24 per (row, incident element)
-                                run_start[n_runs]  CSR offset of the first entry of a run of consecutive rows
-                                run_meta[n_runs]   out_base | len<<16                                           */
-  int32_t max_vert, max_elem, max_out, max_blob_words; /* per-tile maxima (shared-memory sizing) */
+  const int32_t* e_off;  /* [n_tiles+1] word offset of each tile's E blob, multiples of 4 */
+  const int32_t* e_blob;
+  const int32_t* l_off;  /* [n_tiles+1] word offset of each tile's L blob, multiples of 4 */
+  const int32_t* l_blob;
+  int32_t max_vert, max_elem, max_e_words, max_l_words; /* per-tile maxima (shared-memory sizing) */
+  int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = choose from max_elem */
+  int32_t elem_stride;      /* row length of the local-matrix table, >= max_elem, multiple of 32 */
 } tfem_tile_plan;
 
 int tfem_abi_version(void);

@@ -16,7 +16,8 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 import torch
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libtfem_b200.so")
+# TFEM_B200_LIB selects another build of the same ABI (profiling variants); default: the in-tree library
+LIB_PATH = os.environ.get("TFEM_B200_LIB") or os.path.join(PKG, "lib", "libtfem_b200.so")
 HEADER = os.path.join(os.path.dirname(PKG), "include", "tfem_b200.h")
 
 TFEM_SRC_NONE, TFEM_SRC_SAMPLED, TFEM_SRC_CONST, TFEM_SRC_SINSIN = 0, 1, 2, 3
@@ -43,12 +44,16 @@ class TilePlan(Structure):
 
     _fields_ = [
         ("n_tiles", c_int64),
-        ("tile_off", c_void_p),
-        ("blob", c_void_p),
+        ("e_off", c_void_p),
+        ("e_blob", c_void_p),
+        ("l_off", c_void_p),
+        ("l_blob", c_void_p),
         ("max_vert", c_int32),
         ("max_elem", c_int32),
-        ("max_out", c_int32),
-        ("max_blob_words", c_int32),
+        ("max_e_words", c_int32),
+        ("max_l_words", c_int32),
+        ("consumer_threads", c_int32),
+        ("elem_stride", c_int32),
     ]
 
 

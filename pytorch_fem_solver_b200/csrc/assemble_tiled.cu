@@ -11,15 +11,17 @@
 //
 //   producer warp (1 warp)                       consumer warps (8 warps)
 //   ------------------------------------------   ------------------------------------------------
-//   TMA bulk copy of the blob of tile t+2        wait full[t]
-//   (cp.async.bulk + mbarrier complete_tx)       A  rotate the tile's base sin/cos to every vertex
-//   wait blob t+1                                B  integrate every tile element ONCE: 6 matrix
-//   cp.async gather of the vertex coordinates       entries (symmetric form) + 3 load entries
-//   of tile t+1 (16 B per vertex) -> shared      C  one thread per owned row sums its incident
-//   full-range sin/cos at ONE base vertex           elements in increasing element order into a
-//   arrive full[t+1]                                 shared image of the row (no atomics)
-//                                                D  stream the image to csr_val in runs of
-//                                                   consecutive rows (coalesced 8 B stores)
+//   TMA bulk copies (cp.async.bulk + mbarrier     wait full[t]
+//   complete_tx) of the E blob of tile t+2 and   A  rotate the tile's base sin/cos to every vertex
+//   the L blob of tile t+1                       B  integrate every tile element ONCE: 6 matrix
+//   wait E blob t+1                                 entries (symmetric form) + 3 load entries
+//   cp.async gather of the vertex coordinates       -> shared
+//   of tile t+1 (16 B per vertex) -> shared      C  one thread per CSR ENTRY of the tile sums the
+//   full-range sin/cos at ONE base vertex           entry's contributions in increasing element
+//   arrive full[t+1]                                 order (no atomics, no read-modify-write) and
+//                                                   stores it: consecutive threads write
+//                                                   consecutive csr_val slots (coalesced);
+//                                                   one thread per owned row does the load entry
 //                                                arrive done[t]
 //
 // so global-memory latency (blob, coordinate gather) and the only library sin/cos of a tile are
@@ -28,6 +30,39 @@
 // Elements on a tile border are recomputed by the neighbouring tile (halo ~15%).
 // HBM traffic is coords + index blob + outputs, each touched once.
 #include "common.cuh"
+
+// Profiling aid (never set in the shipped build): -DTFEM_DEBUG_SKIP=<mask> removes phases so their
+// share of the kernel time can be measured; 1 = A (vertex sin/cos), 2 = B (integration), 4 = C,
+// 8 = keep C's arithmetic but suppress its global stores.
+#ifndef TFEM_DEBUG_SKIP
+#define TFEM_DEBUG_SKIP 0
+#endif
+// tuning knobs of the shipped build (overridable for experiments)
+#ifndef TFEM_L_STAGES
+#define TFEM_L_STAGES 1  // one L buffer: refilled while the next tile integrates; leaves room for 3 CTAs/SM
+#endif
+#ifndef TFEM_MIN_CTAS
+#define TFEM_MIN_CTAS 3  // resident CTAs per SM of the 256-consumer build (caps registers at 72)
+#endif
+#ifndef TFEM_MIN_CTAS_128
+#define TFEM_MIN_CTAS_128 5
+#endif
+
+// -DTFEM_DEBUG_TIMING: consumer thread 0 / producer lane 0 of a few CTAs print the cycles they spent
+// per phase (summed over the CTA's tiles).  Profiling aid only.
+#ifdef TFEM_DEBUG_TIMING
+#include <cstdio>
+#define TFEM_T_DECL long long t_mark = clock64(), t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TFEM_T(i)                      \
+  do {                                 \
+    const long long t_now = clock64(); \
+    t_acc[i] += t_now - t_mark;        \
+    t_mark = t_now;                    \
+  } while (0)
+#else
+#define TFEM_T_DECL
+#define TFEM_T(i)
+#endif
 
 namespace tfem {
 
@@ -74,9 +109,10 @@ __device__ __forceinline__ void consumer_sync() {
 }
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
-constexpr int kBlobHeader = 8;
-constexpr int kBlobStages = 3;
-constexpr int kSmemHeader = 256;  // mbarriers (7 x 8 B) + two base-point records (2 x 6 values)
+constexpr int kBlobHeader = 12;
+constexpr int kEStages = 3;       // E blobs in flight
+constexpr int kLStages = TFEM_L_STAGES;  // L blobs in flight
+constexpr int kSmemHeader = 256;  // mbarriers (9 x 8 B) + two base-point records (2 x 6 values)
 
 template <int ORDER> struct NQ;
 template <> struct NQ<1> { static constexpr int value = 1; };
@@ -128,65 +164,85 @@ __device__ __forceinline__ void sincos_about(T w, T x, T xb, T sb, T cb, T& s, T
   }
 }
 
-struct BlobView {
-  int n_vert, n_elem, n_rows, n_runs, n_corner, n_out, base_vertex;
+struct EView {  // "early" blob: header + vertices + connectivity
+  int n_vert, n_elem, n_rows, n_runs, n_out, n_contrib, base_vertex, n_lcontrib, n_heavy;
   const int32_t* vert;
   const uint32_t* elem;
-  const int32_t* row_id;
-  const int32_t* row_meta;
-  const int32_t* row_cptr;
-  const uint32_t* corner;
-  const int32_t* run_start;
-  const int32_t* run_meta;
 };
 
-__device__ __forceinline__ BlobView view_blob(const int32_t* b) {
-  BlobView v;
-  v.n_vert = b[0]; v.n_elem = b[1]; v.n_rows = b[2]; v.n_runs = b[3]; v.n_corner = b[4]; v.n_out = b[5];
-  v.base_vertex = b[6];
+__device__ __forceinline__ EView view_e(const int32_t* b) {
+  EView v;
+  v.n_vert = b[0]; v.n_elem = b[1]; v.n_rows = b[2]; v.n_runs = b[3];
+  v.n_out = b[4]; v.n_contrib = b[5]; v.base_vertex = b[6]; v.n_lcontrib = b[7]; v.n_heavy = b[8];
   v.vert = b + kBlobHeader;
   v.elem = reinterpret_cast<const uint32_t*>(v.vert + pad4(v.n_vert));
-  v.row_id = reinterpret_cast<const int32_t*>(v.elem + pad4(v.n_elem));
-  v.row_meta = v.row_id + pad4(v.n_rows);
-  v.row_cptr = v.row_meta + pad4(v.n_rows);
-  v.corner = reinterpret_cast<const uint32_t*>(v.row_cptr + pad4(v.n_rows + 1));
-  v.run_start = reinterpret_cast<const int32_t*>(v.corner + pad4(v.n_corner));
-  v.run_meta = v.run_start + pad4(v.n_runs);
+  return v;
+}
+
+struct LView {  // "late" blob: rows, runs and per-entry contribution lists
+  const int32_t* row_id;
+  const int32_t* run_start;
+  const int32_t* run_meta;
+  const uint16_t* ent_seg;
+  const uint16_t* contrib;
+  const uint16_t* lrow_seg;
+  const uint16_t* lcontrib;
+  const uint32_t* row_diag;
+  const uint16_t* heavy;
+  const uint32_t* heavy_pos;
+};
+
+__device__ __forceinline__ LView view_l(const int32_t* b, const EView& e) {
+  LView v;
+  v.row_id = b;
+  v.run_start = v.row_id + pad4(e.n_rows);
+  v.run_meta = v.run_start + pad4(e.n_runs);
+  const int32_t* p = v.run_meta + pad4(e.n_runs);
+  v.ent_seg = reinterpret_cast<const uint16_t*>(p);
+  p += pad4((e.n_out + 2) >> 1);
+  v.contrib = reinterpret_cast<const uint16_t*>(p);
+  p += pad4((e.n_contrib + 1) >> 1);
+  v.lrow_seg = reinterpret_cast<const uint16_t*>(p);
+  p += pad4((e.n_rows + 2) >> 1);
+  v.lcontrib = reinterpret_cast<const uint16_t*>(p);
+  p += pad4((e.n_lcontrib + 1) >> 1);
+  v.row_diag = reinterpret_cast<const uint32_t*>(p);
+  p += pad4(e.n_rows);
+  v.heavy = reinterpret_cast<const uint16_t*>(p);
+  p += pad4((e.n_heavy + 1) >> 1);
+  v.heavy_pos = reinterpret_cast<const uint32_t*>(p);
   return v;
 }
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
-__global__ void __launch_bounds__(CONSUMERS + 32, 2) assemble_tiled_kernel(
-    const int n_tiles, const int32_t* __restrict__ tile_off, const int32_t* __restrict__ blob,
-    const int max_vert, const int elem_stride, const int max_out, const int max_blob_words,
-    const T* __restrict__ coords, const QuadT<T> quad, const T alpha, const T beta, const SourceT<T> src,
-    T* __restrict__ csr_val, T* __restrict__ load) {
+__global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_CTAS_128 : (CONSUMERS == 256 ? TFEM_MIN_CTAS : 2))) assemble_tiled_kernel(
+    const int n_tiles, const int32_t* __restrict__ e_off, const int32_t* __restrict__ e_blob,
+    const int32_t* __restrict__ l_off, const int32_t* __restrict__ l_blob, const int max_vert,
+    const int elem_stride, const int e_words, const int l_words, const T* __restrict__ coords,
+    const QuadT<T> quad, const T alpha, const T beta, const SourceT<T> src, T* __restrict__ csr_val,
+    T* __restrict__ load) {
   constexpr int NQV = NQ<ORDER>::value;
   constexpr bool HAS_LOAD = SRC != TFEM_SRC_NONE;
   constexpr bool SINSIN = SRC == TFEM_SRC_SINSIN;
   using V2 = typename Vec2<T>::type;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ header | blob x3 | vertex coordinates x2 | sin/cos fields | sloc[9][elem_stride] | sout ]
-  uint64_t* blob_bar = reinterpret_cast<uint64_t*>(smem_raw);  // [3] TMA landed
-  uint64_t* full_bar = blob_bar + kBlobStages;                 // [2] tile staged (coords + base point)
-  uint64_t* done_bar = full_bar + 2;                           // [2] consumers finished the tile
-  T* sbase = reinterpret_cast<T*>(smem_raw + 64);              // [2][6] bx, by, sin/cos(w bx), sin/cos(w by)
-  int32_t* sblob = reinterpret_cast<int32_t*>(smem_raw + kSmemHeader);
-  V2* vxy = reinterpret_cast<V2*>(sblob + kBlobStages * max_blob_words);  // [2][max_vert]
-  T* trig = reinterpret_cast<T*>(vxy + 2 * max_vert);                     // [4][max_vert]
-  T* sloc = trig + (SINSIN ? 4 : 0) * max_vert;
-  T* sout = sloc + 9 * elem_stride;
-  (void)max_out;
+  // [ header | E blob x3 | L blob x2 | vertex coordinates x2 | sin/cos fields | sloc[9][elem_stride] ]
+  uint64_t* e_bar = reinterpret_cast<uint64_t*>(smem_raw);  // [3] E blob landed
+  uint64_t* l_bar = e_bar + kEStages;                       // [2] L blob landed
+  uint64_t* full_bar = l_bar + kLStages;                    // [2] tile staged (coords + base point)
+  uint64_t* done_bar = full_bar + 2;                        // [2] consumers finished the tile
+  T* sbase = reinterpret_cast<T*>(smem_raw + 128);          // [2][6] bx, by, sin/cos(w bx), sin/cos(w by)
+  int32_t* s_e = reinterpret_cast<int32_t*>(smem_raw + kSmemHeader);
+  int32_t* s_l = s_e + kEStages * e_words;
+  V2* vxy = reinterpret_cast<V2*>(s_l + kLStages * l_words);  // [2][max_vert]
+  T* trig = reinterpret_cast<T*>(vxy + 2 * max_vert);         // [4][max_vert]
+  T* sloc = trig + (SINSIN ? 4 : 0) * max_vert;               // [9][elem_stride]
 
   const int tid = threadIdx.x;
   const int n_local = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   if (tid == 0) {
-    for (int i = 0; i < kBlobStages; ++i) mbar_init(blob_bar + i, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(full_bar + i, 1);
-      mbar_init(done_bar + i, 1);
-    }
+    for (int i = 0; i < kEStages + kLStages + 4; ++i) mbar_init(e_bar + i, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -194,31 +250,43 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 2) assemble_tiled_kernel(
   if (tid >= CONSUMERS) {
     // =================================== producer warp =======================================
     const int lane = tid - CONSUMERS;
-    auto issue_blob = [&](int it) {
+    auto issue_e = [&](int it) {
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const int off0 = __ldg(tile_off + tile);
-      const uint32_t bytes = (uint32_t)(__ldg(tile_off + tile + 1) - off0) * 4u;
-      const int slot = it % kBlobStages;
-      mbar_expect_tx(blob_bar + slot, bytes);
-      bulk_g2s(sblob + slot * max_blob_words, blob + off0, bytes, blob_bar + slot);
+      const int off0 = __ldg(e_off + tile);
+      const uint32_t bytes = (uint32_t)(__ldg(e_off + tile + 1) - off0) * 4u;
+      const int slot = it % kEStages;
+      mbar_expect_tx(e_bar + slot, bytes);
+      bulk_g2s(s_e + slot * e_words, e_blob + off0, bytes, e_bar + slot);
+    };
+    auto issue_l = [&](int it) {
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int off0 = __ldg(l_off + tile);
+      const uint32_t bytes = (uint32_t)(__ldg(l_off + tile + 1) - off0) * 4u;
+      const int slot = it % kLStages;
+      mbar_expect_tx(l_bar + slot, bytes);
+      bulk_g2s(s_l + slot * l_words, l_blob + off0, bytes, l_bar + slot);
     };
     if (lane == 0) {
-      issue_blob(0);
-      if (n_local > 1) issue_blob(1);
+      issue_e(0);
+      issue_l(0);
+      if (n_local > 1) issue_e(1);
     }
+    TFEM_T_DECL;
     for (int it = 0; it < n_local; ++it) {
-      const int slot = it % kBlobStages, buf = it & 1;
+      const int slot = it % kEStages, buf = it & 1;
       // stage tile `it` while the consumers work on tile it-1: vxy[buf] / sbase[buf] were last
       // read by tile it-2
       if (it >= 2) mbar_wait(done_bar + (it & 1), ((it - 2) >> 1) & 1);
-      mbar_wait(blob_bar + slot, (it / kBlobStages) & 1);
-      const BlobView bv = view_blob(sblob + slot * max_blob_words);
+      TFEM_T(0);
+      mbar_wait(e_bar + slot, (it / kEStages) & 1);
+      TFEM_T(1);
+      const EView ev = view_e(s_e + slot * e_words);
       V2* dst = vxy + buf * max_vert;
-      for (int i = lane; i < bv.n_vert; i += 32)
-        cp_async<(int)sizeof(V2)>(dst + i, reinterpret_cast<const V2*>(coords) + bv.vert[i]);
+      for (int i = lane; i < ev.n_vert; i += 32)
+        cp_async<(int)sizeof(V2)>(dst + i, reinterpret_cast<const V2*>(coords) + ev.vert[i]);
       if constexpr (SINSIN) {
         T bx, by, sx, cx, sy, cy;
-        load_xy(coords, bv.base_vertex, bx, by);
+        load_xy(coords, ev.base_vertex, bx, by);
         sincos_full(src.p1 * bx, sx, cx);
         sincos_full(src.p2 * by, sy, cy);
         if (lane == 0) {
@@ -226,31 +294,48 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 2) assemble_tiled_kernel(
           sb[0] = bx; sb[1] = by; sb[2] = sx; sb[3] = cx; sb[4] = sy; sb[5] = cy;
         }
       }
+      TFEM_T(2);
       cp_async_wait_all();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + buf);
-      // the blob slot of tile it+2 is the one tile it-1 used: refill it once that tile is done
-      if (it + 2 < n_local) {
-        if (it >= 1) mbar_wait(done_bar + ((it - 1) & 1), ((it - 1) >> 1) & 1);
-        if (lane == 0) issue_blob(it + 2);
+      TFEM_T(3);
+      if (kLStages == 1 && it >= 1) {  // single L buffer: refill it for tile `it` once tile it-1 is done
+        mbar_wait(done_bar + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        if (lane == 0) issue_l(it);
       }
+      // E slot of tile it+2 and L slot of tile it+1 are the ones tile it-1 used
+      if (it + 1 < n_local) {
+        if (it >= 1) mbar_wait(done_bar + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        if (lane == 0) {
+          if (kLStages >= 2) issue_l(it + 1);
+          if (it + 2 < n_local) issue_e(it + 2);
+        }
+      }
+      TFEM_T(4);
     }
+#ifdef TFEM_DEBUG_TIMING
+    if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 151))
+      printf("cta %d producer (%d tiles): wait done(it-2) %lld | wait E %lld | issue gather + base sincos %lld | gather landed %lld | wait done(it-1)+issue %lld\n",
+             (int)blockIdx.x, n_local, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[4]);
+#endif
     return;
   }
 
   // ===================================== consumer warps ========================================
+  TFEM_T_DECL;
   for (int it = 0; it < n_local; ++it) {
-    const int slot = it % kBlobStages, buf = it & 1;
+    const int slot = it % kEStages, buf = it & 1;
     mbar_wait(full_bar + buf, (it >> 1) & 1);
-    mbar_wait(blob_bar + slot, (it / kBlobStages) & 1);  // TMA writes visible to this thread too
-    const BlobView bv = view_blob(sblob + slot * max_blob_words);
+    TFEM_T(0);
+    mbar_wait(e_bar + slot, (it / kEStages) & 1);  // TMA writes visible to this thread too
+    const EView ev = view_e(s_e + slot * e_words);
     const V2* xy = vxy + buf * max_vert;
 
     // ---- A: sin/cos of the source phase at every tile vertex, rotated from the base vertex ----
     if constexpr (SINSIN) {
       const T* sb = sbase + 6 * buf;
       const T bx = sb[0], by = sb[1], sbx = sb[2], cbx = sb[3], sby = sb[4], cby = sb[5];
-      for (int i = tid; i < bv.n_vert; i += CONSUMERS) {
+      for (int i = tid; i < ((TFEM_DEBUG_SKIP & 1) ? 0 : ev.n_vert); i += CONSUMERS) {
         const V2 p = xy[i];
         T s, c;
         sincos_about(src.p1, p.x, bx, sbx, cbx, s, c);
@@ -260,15 +345,13 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 2) assemble_tiled_kernel(
         trig[2 * max_vert + i] = s;
         trig[3 * max_vert + i] = c;
       }
+      consumer_sync<CONSUMERS>();
     }
-    if constexpr (HAS_MAT) {
-      for (int i = tid; i < bv.n_out; i += CONSUMERS) sout[i] = T(0);
-    }
-    if constexpr (SINSIN || HAS_MAT) consumer_sync<CONSUMERS>();
 
+    TFEM_T(1);
     // ---- B: local matrices and loads, each tile element once ----------------------------------
-    for (int el = tid; el < bv.n_elem; el += CONSUMERS) {
-      const uint32_t packed = bv.elem[el];
+    for (int el = tid; el < ((TFEM_DEBUG_SKIP & 2) ? 0 : ev.n_elem); el += CONSUMERS) {
+      const uint32_t packed = ev.elem[el];
       const int a = packed & 1023u, b = (packed >> 10) & 1023u, c = (packed >> 20) & 1023u;
       const V2 p0 = xy[a], p1 = xy[b], p2 = xy[c];
       const T x0 = p0.x, y0 = p0.y;
@@ -338,60 +421,93 @@ __global__ void __launch_bounds__(CONSUMERS + 32, 2) assemble_tiled_kernel(
     }
     consumer_sync<CONSUMERS>();
 
-    // ---- C: one thread per owned row gathers its corners in increasing element order --------
-    for (int j = tid; j < bv.n_rows; j += CONSUMERS) {
-      const int meta = bv.row_meta[j];
-      const int base = meta & 0xffff, pos_diag = (meta >> 16) & 0xff;
-      const int c0 = bv.row_cptr[j], c1 = bv.row_cptr[j + 1];
-      T diag = T(0), rhs = T(0);
-      for (int cidx = c0; cidx < c1; ++cidx) {
-        const uint32_t cw = bv.corner[cidx];
-        const int el = cw & 0xfffu, k = (cw >> 12) & 3u;
-        if constexpr (HAS_MAT) {
-          const int pa = (cw >> 16) & 0xffu, pb = cw >> 24;
-          const int kb = k == 0 ? 2 : k - 1;  // (k+2) % 3
-          diag += sloc[k * elem_stride + el];
-          sout[base + pa] += sloc[(3 + k) * elem_stride + el];   // entry (k+1, k)
-          sout[base + pb] += sloc[(3 + kb) * elem_stride + el];  // entry (k+2, k)
+    TFEM_T(2);
+    // ---- C: one thread per CSR entry / per load entry; contributions in increasing element id --
+    mbar_wait(l_bar + (it % kLStages), (it / kLStages) & 1);
+    TFEM_T(3);
+    const LView lv = view_l(s_l + (it % kLStages) * l_words, ev);
+    auto store = [&](int64_t pos, T value) {
+      if (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30)) csr_val[pos] = value;
+    };
+    if constexpr (HAS_MAT) {
+      // Entries with <= 2 contributions (every off-diagonal of a manifold mesh): one warp per run of
+      // consecutive rows, lane i takes entries i, i+32, ... of the run, so a warp store covers 32
+      // consecutive csr_val slots; two entries per lane are kept in flight.
+      const int lane = tid & 31, warp = tid >> 5;
+      for (int r = warp; r < ((TFEM_DEBUG_SKIP & 4) ? 0 : ev.n_runs); r += CONSUMERS / 32) {
+        const int meta = lv.run_meta[r];
+        const int base = meta & 0xffff, len = (meta >> 16) & 0xffff;
+        const int64_t gpos = lv.run_start[r];
+        for (int i = lane; i < len; i += 64) {
+          const int i1 = i + 32;
+          const bool two = i1 < len;
+          const int oa = base + i, ob = base + (two ? i1 : i);
+          const int sa = lv.ent_seg[oa], na = lv.ent_seg[oa + 1] - sa;
+          const int sb = lv.ent_seg[ob], nb = lv.ent_seg[ob + 1] - sb;
+          const int ca0 = lv.contrib[na > 0 ? sa : 0], ca1 = lv.contrib[na > 1 ? sa + 1 : 0];
+          const int cb0 = lv.contrib[nb > 0 ? sb : 0], cb1 = lv.contrib[nb > 1 ? sb + 1 : 0];
+          const T va0 = sloc[ca0], va1 = sloc[ca1], vb0 = sloc[cb0], vb1 = sloc[cb1];
+          T acc_a = na > 0 ? va0 : T(0), acc_b = nb > 0 ? vb0 : T(0);
+          if (na > 1) acc_a += va1;
+          if (nb > 1) acc_b += vb1;
+          if (na <= 2) store(gpos + i, acc_a);
+          if (two && nb <= 2) store(gpos + i1, acc_b);
         }
-        if constexpr (HAS_LOAD) rhs += sloc[(6 + k) * elem_stride + el];
+      }
+      TFEM_T(6);
+      // the few other entries with > 2 contributions (non-manifold edges, degenerate elements)
+      for (int h = tid; h < ((TFEM_DEBUG_SKIP & 4) ? 0 : ev.n_heavy); h += CONSUMERS) {
+        const int o = lv.heavy[h];
+        T acc = T(0);
+        for (int s = lv.ent_seg[o]; s < lv.ent_seg[o + 1]; ++s) acc += sloc[lv.contrib[s]];
+        store(lv.heavy_pos[h], acc);
+      }
+    }
+    TFEM_T(7);
+    // one thread per owned row: its load entry and its diagonal share one element list
+    for (int j = tid; j < ((TFEM_DEBUG_SKIP & 4) ? 0 : ev.n_rows); j += CONSUMERS) {
+      const int s0 = lv.lrow_seg[j], s1 = lv.lrow_seg[j + 1];
+      T rhs = T(0), diag = T(0);
+      for (int s = s0; s < s1; ++s) {
+        const int code = lv.lcontrib[s];  // k*elem_stride + element
+        if constexpr (HAS_LOAD) rhs += sloc[code + 6 * elem_stride];
+        if constexpr (HAS_MAT) diag += sloc[code];
+      }
+      if constexpr (HAS_LOAD) {
+        if (!(TFEM_DEBUG_SKIP & 8) || rhs == T(1.2345e30)) load[lv.row_id[j]] = rhs;
       }
       if constexpr (HAS_MAT) {
-        if (c1 > c0) sout[base + pos_diag] += diag;
-      }
-      if constexpr (HAS_LOAD) load[bv.row_id[j]] = rhs;
-    }
-
-    // ---- D: stream the row images out, one warp per run of consecutive rows ------------------
-    if constexpr (HAS_MAT) {
-      consumer_sync<CONSUMERS>();
-      const int lane = tid & 31, warp = tid >> 5;
-      for (int r = warp; r < bv.n_runs; r += CONSUMERS / 32) {
-        const int gstart = bv.run_start[r];
-        const int meta = bv.run_meta[r];
-        const int base = meta & 0xffff, len = (meta >> 16) & 0xffff;
-        for (int i = lane; i < len; i += 32) csr_val[(int64_t)gstart + i] = sout[base + i];
+        const uint32_t pos = lv.row_diag[j];
+        if (pos != 0xffffffffu) store(pos, diag);
       }
     }
-    consumer_sync<CONSUMERS>();  // sloc / sout / trig / blob slot free for the next tile
+    TFEM_T(4);
+    consumer_sync<CONSUMERS>();  // sloc / trig / blob slots free for the next tile
     if (tid == 0) mbar_arrive(done_bar + buf);
+    TFEM_T(5);
   }
+#ifdef TFEM_DEBUG_TIMING
+  if ((tid == 0 || tid == 255) && (blockIdx.x == 0 || blockIdx.x == 151))
+    printf("cta %d consumer t%d (%d tiles): wait full %lld | A+sync %lld | B+sync %lld | wait L %lld | C light %lld heavy %lld rows %lld | end sync %lld\n",
+           (int)blockIdx.x, tid, n_local, t_acc[0], t_acc[1], t_acc[2], t_acc[3], t_acc[6], t_acc[7], t_acc[4], t_acc[5]);
+#endif
 }
 
 template <typename T>
-size_t tiled_smem_bytes(const tfem_tile_plan* hp, int src_kind, int* elem_stride, int* blob_words) {
+size_t tiled_smem_bytes(const tfem_tile_plan* hp, int src_kind, int* elem_stride, int* e_words, int* l_words) {
   const int trig_fields = src_kind == TFEM_SRC_SINSIN ? 4 : 0;
-  *elem_stride = (hp->max_elem + 31) & ~31;
-  *blob_words = (hp->max_blob_words + 3) & ~3;
-  return kSmemHeader + 4 * (size_t)kBlobStages * *blob_words +
-         sizeof(T) * ((size_t)(4 + trig_fields) * hp->max_vert + (size_t)9 * *elem_stride + (size_t)hp->max_out);
+  *elem_stride = hp->elem_stride;
+  *e_words = (hp->max_e_words + 3) & ~3;
+  *l_words = (hp->max_l_words + 3) & ~3;
+  return kSmemHeader + 4 * ((size_t)kEStages * *e_words + (size_t)kLStages * *l_words) +
+         sizeof(T) * ((size_t)(4 + trig_fields) * hp->max_vert + (size_t)9 * *elem_stride);
 }
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
 int launch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad, T alpha, T beta,
                  const SourceT<T>& src, T* csr_val, T* load, cudaStream_t s) {
-  int elem_stride = 0, blob_words = 0;
-  const size_t smem = tiled_smem_bytes<T>(hp, SRC, &elem_stride, &blob_words);
+  int elem_stride = 0, e_words = 0, l_words = 0;
+  const size_t smem = tiled_smem_bytes<T>(hp, SRC, &elem_stride, &e_words, &l_words);
   if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
   auto kern = assemble_tiled_kernel<T, CONSUMERS, ORDER, SRC, HAS_MAT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -403,8 +519,8 @@ int launch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad
     return TFEM_ERR_LAUNCH;
   const int64_t resident = (int64_t)sms * per_sm;  // persistent grid: every CTA is co-resident
   const unsigned grid = (unsigned)(hp->n_tiles < resident ? hp->n_tiles : resident);
-  kern<<<grid, CONSUMERS + 32, smem, s>>>((int)hp->n_tiles, hp->tile_off, hp->blob, hp->max_vert, elem_stride,
-                                         hp->max_out, blob_words, coords, quad, alpha, beta, src, csr_val, load);
+  kern<<<grid, CONSUMERS + 32, smem, s>>>((int)hp->n_tiles, hp->e_off, hp->e_blob, hp->l_off, hp->l_blob, hp->max_vert,
+                                         elem_stride, e_words, l_words, coords, quad, alpha, beta, src, csr_val, load);
   return check_launch();
 }
 
@@ -429,8 +545,9 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   if (hp->n_tiles == 0) return TFEM_OK;
   if (!coords || (!csr_val && !load)) return TFEM_ERR_BAD_ARG;
   if (csr_val && !form) return TFEM_ERR_BAD_ARG;
-  if (!hp->tile_off || !hp->blob) return TFEM_ERR_BAD_ARG;
-  if (hp->max_vert > 1024 || hp->max_elem > 4096 || hp->max_out > 65535) return TFEM_ERR_TOO_LARGE;
+  if (!hp->e_off || !hp->e_blob || !hp->l_off || !hp->l_blob) return TFEM_ERR_BAD_ARG;
+  if (hp->max_vert > 1024 || hp->max_elem > 4096 || hp->elem_stride < hp->max_elem || 9 * hp->elem_stride > 65535)
+    return TFEM_ERR_TOO_LARGE;
   if (hp->n_tiles > kMaxIndex) return TFEM_ERR_TOO_LARGE;
   if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
   SourceT<T> src = make_source<T>(source);
@@ -443,13 +560,22 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   const QuadT<T> quad = make_quad<T>(quad_order);
   const T alpha = form ? T(form->alpha) : T(0), beta = form ? T(form->beta) : T(0);
   auto s = static_cast<cudaStream_t>(stream);
-  constexpr int CONSUMERS = 256;
-  switch (quad_order) {
-    case 1: return dispatch_tiled<T, CONSUMERS, 1>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
-    case 2: return dispatch_tiled<T, CONSUMERS, 2>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
-    case 3: return dispatch_tiled<T, CONSUMERS, 3>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
-    default: return dispatch_tiled<T, CONSUMERS, 4>(hp, coords, quad, alpha, beta, src, csr_val, load, s);
+  // consumer threads per CTA: one tile element per thread where the tile allows it
+  int consumers = hp->consumer_threads;
+  if (consumers == 0) consumers = 256;  // measured best on B200 with ~160-row tiles (3 CTAs/SM); 128/384/512 selectable
+#define TFEM_DISPATCH_ORDER(C)                                                                             \
+  switch (quad_order) {                                                                                    \
+    case 1: return dispatch_tiled<T, C, 1>(hp, coords, quad, alpha, beta, src, csr_val, load, s);         \
+    case 2: return dispatch_tiled<T, C, 2>(hp, coords, quad, alpha, beta, src, csr_val, load, s);         \
+    case 3: return dispatch_tiled<T, C, 3>(hp, coords, quad, alpha, beta, src, csr_val, load, s);         \
+    default: return dispatch_tiled<T, C, 4>(hp, coords, quad, alpha, beta, src, csr_val, load, s);        \
   }
+  if (consumers == 128) { TFEM_DISPATCH_ORDER(128) }
+  if (consumers == 256) { TFEM_DISPATCH_ORDER(256) }
+  if (consumers == 384) { TFEM_DISPATCH_ORDER(384) }
+  if (consumers == 512) { TFEM_DISPATCH_ORDER(512) }
+#undef TFEM_DISPATCH_ORDER
+  return TFEM_ERR_BAD_ARG;
 }
 
 }  // namespace tfem

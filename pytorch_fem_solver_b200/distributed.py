@@ -181,7 +181,7 @@ def strip_mesh(nx: int, ny: int, rank: int, world: int, jitter: float = 0.25, se
 class StripAssembly:
     """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip."""
 
-    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=216, group=None, exchange_ops=None):
+    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=160, group=None, exchange_ops=None):
         import numpy as np
 
         from . import ElementTri, MeshTri
