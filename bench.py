@@ -63,6 +63,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json); only valid for the configuration that was profiled."""
+    path = os.path.join(REPO, "profiles", "roofline_traffic.json")
+    if args.path != "tiled" or (args.nx, args.ny) != (NX, NY) or not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get("traffic_bytes_per_launch")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML; only samples taken while `active`
     (the timed region) are reported."""
@@ -353,7 +363,7 @@ def run_ours(args):
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": None,
+                "traffic": ncu_traffic(args),
                 "peak_source": peak_source,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "kernel": "assemble_tiled_kernel<double,256,true,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
