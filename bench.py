@@ -197,6 +197,8 @@ def workload_config(args):
         "path": args.path,
         "l2": "flushed between timed steps (256 MiB write)",
         "symbolic": "CSR pattern + tile plan built once, outside the timed region",
+        "multi_gpu": "weak scaling: one strip of the same size per GPU, interface rows packed, all-gathered over NCCL and "
+        "added by their owners on a side stream while the interior tiles assemble",
     }
 
 
@@ -252,7 +254,11 @@ def run_ours(args):
 
         kernels_per_step = 3
 
-    if assembler is not None:
+    if assembler is not None and args.path == "tiled":
+        # interface tiles first, then interior tiles while the NCCL exchange runs on a side stream
+        step = assembler.step
+        kernels_per_step = 2 + assembler.fused_exchange.n_kernels
+    elif assembler is not None:
 
         def step():
             local_step()
@@ -283,8 +289,6 @@ def run_ours(args):
     sampler.active = True
     for i in range(args.steps):
         flush.fill_(float(i))  # evict L2 (126 MB) between timed steps; outside the event pair
-        if world > 1:
-            dist.barrier()
         starts[i].record()
         step()
         ends[i].record()
@@ -314,11 +318,21 @@ def run_ours(args):
         values_host = torch.empty(nnz, dtype=torch.float64).pin_memory()
         load_host = torch.empty((n_v, 1), dtype=torch.float64).pin_memory()
 
-        if assembler is not None:
-            basis._post_assemble_hook = assembler.exchange  # interface rows summed before the device->host copy
+        if assembler is not None and args.path == "tiled":
 
-        def e2e_step():
-            basis.assemble_from_host(coords_host, bilinear, load_form, values_host, load_host, path=args.path)
+            def e2e_step():  # host coordinates in, distributed assembly, owned values + load back to the host
+                lay.coords.copy_(coords_host, non_blocking=True)
+                assembler.step()
+                values_host.copy_(assembler.values, non_blocking=True)
+                load_host.copy_(assembler.load.reshape(load_host.shape), non_blocking=True)
+
+        else:
+            if assembler is not None:
+                basis._post_assemble_hook = assembler.exchange  # interface rows summed before the device->host copy
+
+            def e2e_step():
+                basis.assemble_from_host(coords_host, bilinear, load_form, values_host, load_host, path=args.path)
+
         for _ in range(3):
             e2e_step()
         barrier()
@@ -382,7 +396,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": e2e["h2d"],
                 "d2h_bytes_per_step": e2e["d2h"],
                 "ms_per_step": e2e_step_s * 1e3,
-                "api": "Basis.assemble_from_host(pinned coords, StiffnessMass, Load, pinned values, pinned load)",
+                "api": "Basis.assemble_from_host(pinned coords, StiffnessMass, Load, pinned values, pinned load)" if world == 1
+                else "StripAssembly.step() between pinned-host copies of coordinates in and owned CSR values + load out",
             }
         if world == 1 and not args.no_cpu_baseline:
             cpu_value, sample, timings = cpu_reference_run(args.nx, args.ny, repeats=2)

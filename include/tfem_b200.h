@@ -98,7 +98,9 @@ typedef struct tfem_bilinear {
  *     heavy_pos[n_heavy]   u32  their csr_val positions
  *   Entries with at most two contributions are summed by one thread per entry without a loop.     */
 typedef struct tfem_tile_plan {
-  int64_t n_tiles;
+  int64_t n_tiles;          /* tiles this call processes */
+  const int32_t* tile_list; /* [n_tiles] ids of those tiles, or NULL for tiles 0..n_tiles-1; lets one plan be
+                               run in parts (interface tiles first, interior tiles while the exchange runs) */
   const int32_t* e_off;  /* [n_tiles+1] word offset of each tile's E blob, multiples of 4 */
   const int32_t* e_blob;
   const int32_t* l_off;  /* [n_tiles+1] word offset of each tile's L blob, multiples of 4 */
@@ -106,6 +108,8 @@ typedef struct tfem_tile_plan {
   int32_t max_vert, max_elem, max_e_words, max_l_words; /* per-tile maxima (shared-memory sizing) */
   int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = choose from max_elem */
   int32_t elem_stride;      /* row length of the local-matrix table, >= max_elem, multiple of 32 */
+  int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
+                               (interface pack / NCCL send-recv / add) can run beside it; 0 = use every slot */
 } tfem_tile_plan;
 
 int tfem_abi_version(void);

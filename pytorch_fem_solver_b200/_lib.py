@@ -44,6 +44,7 @@ class TilePlan(Structure):
 
     _fields_ = [
         ("n_tiles", c_int64),
+        ("tile_list", c_void_p),
         ("e_off", c_void_p),
         ("e_blob", c_void_p),
         ("l_off", c_void_p),
@@ -54,6 +55,7 @@ class TilePlan(Structure):
         ("max_l_words", c_int32),
         ("consumer_threads", c_int32),
         ("elem_stride", c_int32),
+        ("reserve_ctas", c_int32),
     ]
 
 

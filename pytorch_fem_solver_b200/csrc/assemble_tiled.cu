@@ -216,7 +216,7 @@ __device__ __forceinline__ LView view_l(const int32_t* b, const EView& e) {
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
 __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_CTAS_128 : (CONSUMERS == 256 ? TFEM_MIN_CTAS : 2))) assemble_tiled_kernel(
-    const int n_tiles, const int32_t* __restrict__ e_off, const int32_t* __restrict__ e_blob,
+    const int n_tiles, const int32_t* __restrict__ tile_list, const int32_t* __restrict__ e_off, const int32_t* __restrict__ e_blob,
     const int32_t* __restrict__ l_off, const int32_t* __restrict__ l_blob, const int max_vert,
     const int elem_stride, const int e_words, const int l_words, const T* __restrict__ coords,
     const QuadT<T> quad, const T alpha, const T beta, const SourceT<T> src, T* __restrict__ csr_val,
@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_C
     // =================================== producer warp =======================================
     const int lane = tid - CONSUMERS;
     auto issue_e = [&](int it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int slot_index = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_list ? __ldg(tile_list + slot_index) : slot_index;
       const int off0 = __ldg(e_off + tile);
       const uint32_t bytes = (uint32_t)(__ldg(e_off + tile + 1) - off0) * 4u;
       const int slot = it % kEStages;
@@ -259,7 +260,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_C
       bulk_g2s(s_e + slot * e_words, e_blob + off0, bytes, e_bar + slot);
     };
     auto issue_l = [&](int it) {
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int slot_index = (int)blockIdx.x + it * (int)gridDim.x;
+      const int tile = tile_list ? __ldg(tile_list + slot_index) : slot_index;
       const int off0 = __ldg(l_off + tile);
       const uint32_t bytes = (uint32_t)(__ldg(l_off + tile + 1) - off0) * 4u;
       const int slot = it % kLStages;
@@ -517,9 +519,10 @@ int launch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CONSUMERS + 32, smem) != cudaSuccess || per_sm < 1)
     return TFEM_ERR_LAUNCH;
-  const int64_t resident = (int64_t)sms * per_sm;  // persistent grid: every CTA is co-resident
+  int64_t resident = (int64_t)sms * per_sm;  // persistent grid: every CTA is co-resident
+  if (hp->reserve_ctas > 0 && resident > hp->reserve_ctas) resident -= hp->reserve_ctas;  // room for concurrent kernels
   const unsigned grid = (unsigned)(hp->n_tiles < resident ? hp->n_tiles : resident);
-  kern<<<grid, CONSUMERS + 32, smem, s>>>((int)hp->n_tiles, hp->e_off, hp->e_blob, hp->l_off, hp->l_blob, hp->max_vert,
+  kern<<<grid, CONSUMERS + 32, smem, s>>>((int)hp->n_tiles, hp->tile_list, hp->e_off, hp->e_blob, hp->l_off, hp->l_blob, hp->max_vert,
                                          elem_stride, e_words, l_words, coords, quad, alpha, beta, src, csr_val, load);
   return check_launch();
 }

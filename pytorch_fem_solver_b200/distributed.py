@@ -17,6 +17,7 @@ Per assembly: pack (tfem_iface_pack) -> batched isend/irecv -> unpack-add (tfem_
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
 
@@ -32,12 +33,18 @@ class ExchangeOps:
 
     pack: Callable[[torch.Tensor, torch.Tensor], torch.Tensor]  # (src, idx) -> src[idx]
     unpack_add: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None]  # dst[idx] += buf
+    pack_into: Callable[[torch.Tensor, torch.Tensor, torch.Tensor], None] = None  # out[:] = src[idx]
+
+    def __post_init__(self):
+        if self.pack_into is None:
+            self.pack_into = lambda out, src, idx: out.copy_(self.pack(src, idx))
 
 
 def cuda_exchange_ops() -> ExchangeOps:
     from . import ops
 
-    return ExchangeOps(pack=ops.gather, unpack_add=ops.unpack_add_)
+    # the per-step calls go straight to the C ABI (a few microseconds of host time each)
+    return ExchangeOps(pack=ops.gather, unpack_add=ops.unpack_add_raw, pack_into=ops.pack_into_raw)
 
 
 def _exchange_variable(send: Dict[int, torch.Tensor], rank: int, world: int, device, dtype, group) -> Dict[int, torch.Tensor]:
@@ -178,13 +185,69 @@ def strip_mesh(nx: int, ny: int, rank: int, world: int, jitter: float = 0.25, se
     return mesh, offset, n_global
 
 
+class FusedExchange:
+    """Interface exchange over ONE device buffer holding `[csr values | load vector]`.
+
+    Every rank packs ALL its outgoing interface entries (for every owner, ascending) with one gather
+    kernel into a fixed-size slot of a send buffer; one `all_gather` moves the slots (interfaces are a
+    few hundred KB, so the redundancy is irrelevant and a single collective keeps the host cost of a
+    step far below the assembly kernel's run time); each owner then adds the slices addressed to it,
+    in ascending peer order, with one add kernel per peer.  Nothing synchronises with the host, so
+    the whole exchange can sit on a side stream while the interior tiles are being assembled."""
+
+    def __init__(self, plan: InterfacePlan, nnz: int, dtype: torch.dtype, device, exchange_ops: Optional[ExchangeOps] = None):
+        self.plan = plan
+        self.ops = exchange_ops or cuda_exchange_ops()
+        world, rank = plan.world, plan.rank
+        combine = lambda pair: torch.cat([pair[0], pair[1] + nnz]).to(torch.int32)  # noqa: E731
+        owners = sorted(plan.send_idx)
+        pieces = [combine(plan.send_idx[o]) for o in owners]
+        self.send_idx = torch.cat(pieces).contiguous() if pieces else torch.zeros(0, dtype=torch.int32, device=device)
+        # table[r, o] = (offset, length) of rank r's entries for owner o inside r's slot
+        table = torch.zeros((world, 2), dtype=torch.int64, device=device)
+        offset = 0
+        for o, piece in zip(owners, pieces):
+            table[o, 0], table[o, 1] = offset, piece.numel()
+            offset += piece.numel()
+        tables = [torch.zeros_like(table) for _ in range(world)]
+        dist.all_gather(tables, table, group=plan.group)
+        slot = torch.tensor([offset], dtype=torch.int64, device=device)
+        dist.all_reduce(slot, op=dist.ReduceOp.MAX, group=plan.group)
+        self.slot = max(int(slot.item()), 1)
+        self.send_buf = torch.zeros(self.slot, dtype=dtype, device=device)
+        self.gathered = torch.zeros((world, self.slot), dtype=dtype, device=device)
+        self.recv = []  # (peer, local positions, offset, length), ascending peer
+        for peer in sorted(plan.recv_idx):
+            off, length = int(tables[peer][rank, 0]), int(tables[peer][rank, 1])
+            idx = combine(plan.recv_idx[peer]).contiguous()
+            assert idx.numel() == length, "interface key lists disagree between sender and owner"
+            self.recv.append((peer, idx, off, length))
+        self.peers = sorted(set(owners) | {p for p, *_ in self.recv})
+        self.bytes_per_exchange = self.send_idx.numel() * self.send_buf.element_size()
+        self.n_kernels = (1 if self.send_idx.numel() else 0) + len(self.recv)
+        self.flat_gather = dist.get_backend(plan.group) == "nccl"
+
+    def __call__(self, buffer: torch.Tensor):
+        if self.send_idx.numel():
+            self.ops.pack_into(self.send_buf[: self.send_idx.numel()], buffer, self.send_idx)
+        if self.flat_gather:
+            dist.all_gather_into_tensor(self.gathered, self.send_buf, group=self.plan.group)
+        else:  # gloo (CPU tests) has no flat all-gather
+            dist.all_gather(list(self.gathered.unbind(0)), self.send_buf, group=self.plan.group)
+        for peer, idx, off, length in self.recv:  # ascending peer order -> bitwise reproducible sums
+            self.ops.unpack_add(buffer, idx, self.gathered[peer, off : off + length])
+
+
 class StripAssembly:
-    """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip."""
+    """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip.
+
+    `step()` assembles the tiles holding interface rows first, then the interior tiles on the main
+    stream while the interface exchange (pack -> NCCL send/recv -> add) runs on a side stream."""
 
     def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=160, group=None, exchange_ops=None):
         import numpy as np
 
-        from . import ElementTri, MeshTri
+        from . import ElementTri, MeshTri, forms
 
         mesh, offset, n_global = strip_mesh(nx, ny, rank, world)
         conn_global = torch.from_numpy(mesh["triangles"].astype(np.int64) + offset).to(device)
@@ -202,6 +265,46 @@ class StripAssembly:
         self.basis._pattern = csr_mod.build_pattern(self.basis._dof_conn_flat(), self.plan.n_local, self.plan.extra_keys)
         self.plan.bind(self.basis.pattern)
         self.exchange = InterfaceExchange(self.plan, exchange_ops)
+
+        # one buffer for [values | load]; interface tiles and interior tiles as two sub-plans
+        pat = self.basis.pattern
+        self.quad_order = quad_order
+        self.buffer = torch.empty(pat.nnz + pat.n_dof, dtype=self.basis.dtype, device=device)
+        self.values, self.load = self.buffer[: pat.nnz], self.buffer[pat.nnz :]
+        self.fused_exchange = FusedExchange(self.plan, pat.nnz, self.basis.dtype, device, exchange_ops)
+        full = self.basis.tile_plan(rows_per_tile)
+        interface_local = torch.searchsorted(self.plan.local_to_global, self.plan.interface_global)
+        is_interface_tile = torch.zeros(full.n_tiles, dtype=torch.bool, device=device)
+        is_interface_tile[full.tile_of_row[interface_local]] = True
+        self.interface_tiles = full.subset(torch.nonzero(is_interface_tile, as_tuple=True)[0])
+        # the interior launch leaves some CTA slots free so the exchange kernels can run beside it
+        reserve = int(os.environ.get("TFEM_RESERVE_CTAS", "24"))
+        self.interior_tiles = full.subset(torch.nonzero(~is_interface_tile, as_tuple=True)[0], reserve_ctas=reserve)
+        self.full_plan = full
+        self.source = forms.SinSinSource()
+        self.side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+
+    def _launch(self, plan, alpha, beta):
+        from . import ops
+
+        ops.assemble_csr_tiled(plan.c_struct(), self.basis._layout.coords, self.quad_order, alpha, beta,
+                               self.source.kind, self.source.params, self.values, self.load)
+
+    def step(self, alpha: float = 1.0, beta: float = 1.0):
+        """One distributed assembly into `self.values` / `self.load` (owned rows complete)."""
+        main = torch.cuda.current_stream()
+        self._launch(self.interface_tiles, alpha, beta)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        # enqueue the long interior launch BEFORE the exchange so the GPU is busy while the host issues
+        # the (comparatively slow to enqueue) pack / all-gather / add sequence on the side stream
+        self._launch(self.interior_tiles, alpha, beta)
+        with torch.cuda.stream(self.side_stream):
+            self.side_stream.wait_event(ready)
+            self.fused_exchange(self.buffer)
+            finished = torch.cuda.Event()
+            finished.record(self.side_stream)
+        main.wait_event(finished)
 
 
 def _basis_for(mesh, element):

@@ -212,6 +212,18 @@ def unpack_add_(dst: Tensor, idx: Tensor, buf: Tensor) -> None:
     call("tfem_iface_unpack_add", dst.dtype, device, idx.shape[0], ptr(idx), ptr(buf), ptr(dst))
 
 
+def pack_into_raw(out: Tensor, src: Tensor, idx: Tensor) -> None:
+    """out[i] = src[idx[i]] into a preallocated buffer: direct C-ABI call for per-step hot loops."""
+    device = check_cuda(out, src, idx)
+    call("tfem_iface_pack", src.dtype, device, idx.shape[0], ptr(idx), ptr(src), ptr(out))
+
+
+def unpack_add_raw(dst: Tensor, idx: Tensor, buf: Tensor) -> None:
+    """dst[idx[i]] += buf[i] (unique idx): direct C-ABI call for per-step hot loops."""
+    device = check_cuda(dst, idx, buf)
+    call("tfem_iface_unpack_add", dst.dtype, device, idx.shape[0], ptr(idx), ptr(buf), ptr(dst))
+
+
 # ------------------------------------------------------------------------------------------------
 # fused named forms
 # ------------------------------------------------------------------------------------------------

@@ -133,17 +133,29 @@ class TilePlan:
     max_out: int
     halo_factor: float  # tile elements / mesh elements (1.0 = every element integrated once)
     index_bytes: int  # bytes of plan data the kernel reads per launch
-    consumer_threads: int = 0  # compute threads per CTA (256 / 384 / 512); 0 = derived from max_elem
+    consumer_threads: int = 0  # compute threads per CTA (128 / 256 / 384 / 512); 0 = library default
+    tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
+    tile_list: torch.Tensor = None  # optional (n,) int32 subset of tiles to run (see `subset`)
+    reserve_ctas: int = 0  # CTA slots left free for kernels on other streams while this plan runs
 
     def c_struct(self) -> "_lib.TilePlan":
         s = _lib.TilePlan()
-        s.n_tiles = self.n_tiles
+        s.n_tiles = self.n_tiles if self.tile_list is None else int(self.tile_list.numel())
+        s.tile_list = None if self.tile_list is None else self.tile_list.data_ptr()
         s.e_off, s.e_blob = self.e_off.data_ptr(), self.e_blob.data_ptr()
         s.l_off, s.l_blob = self.l_off.data_ptr(), self.l_blob.data_ptr()
         s.max_vert, s.max_elem, s.max_e_words, s.max_l_words = self.max_vert, self.max_elem, self.max_e_words, self.max_l_words
         s.elem_stride = self.elem_stride
+        s.reserve_ctas = self.reserve_ctas
         s.consumer_threads = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads))
         return s
+
+    def subset(self, tile_ids: torch.Tensor, reserve_ctas: int = 0) -> "TilePlan":
+        """The same plan restricted to some tiles (shares every array); used to assemble the tiles
+        that hold multi-GPU interface rows first and the rest while the exchange is in flight."""
+        import dataclasses
+
+        return dataclasses.replace(self, tile_list=tile_ids.to(torch.int32).contiguous(), reserve_ctas=reserve_ctas)
 
     def to(self, device) -> "TilePlan":
         moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
@@ -390,4 +402,5 @@ def build_tile_plan(
         max_out=int(n_out.max().item()),
         halo_factor=float(pair_keys.shape[0]) / max(n_el, 1),
         index_bytes=4 * (e_blob.numel() + l_blob.numel() + e_off.numel() + l_off.numel()),
+        tile_of_row=tile_of_row,
     )

@@ -74,7 +74,13 @@ def _worker(rank, world, port, case):
             unpack_add=lambda dst, idx, buf: dst.index_add_(0, idx.long(), buf),
         )
         before = values.clone()
+        load_before = load.clone()
         distributed.InterfaceExchange(plan, ops)(values, load)
+        # the single-buffer / all-gather variant used by StripAssembly.step must give the same bits
+        buffer = torch.cat([before, load_before])
+        fused = distributed.FusedExchange(plan, pattern.nnz, torch.float64, "cpu", ops)
+        fused(buffer)
+        assert torch.equal(buffer[: pattern.nnz], values) and torch.equal(buffer[pattern.nnz :], load)
         again = before.clone()
         distributed.InterfaceExchange(plan, ops)(again, load.clone())
         assert torch.equal(values, again), "owner-side sums must be bitwise reproducible"
