@@ -201,6 +201,18 @@ int tfem_sm_count(void);
                               const int32_t* edge_cells, const int32_t* conn,                      \
                               const T* first_vertex, const T* inv_jac, int d, const T* x_q,        \
                               int n_q, const T* u, T* val, T* grad, void* stream);                 \
+  /* Adjoints of the two interpolations w.r.t. the nodal vector (what autograd derives from the   \
+   * gather + multiply + sum of basis/basis.py:149-159 when the nodal values come from a network,\
+   * examples/example_jump.py:58,75-87).  They produce the per-element / per-(edge, side) part     \
+   * local[., i] = sum_q val_bar[., q] phi_i(q) + sum_c grad_bar[., c] grad phi_i[c];              \
+   * the deterministic scatter (tfem_scatter_linear) then sums it into u_bar.                     \
+   * val_bar / grad_bar may be NULL (treated as zero). */                                         \
+  int tfem_interp_cells_bwd_##SUF(int64_t n_el, const T* v_grad, int d, int quad_order,            \
+                                  const T* val_bar, const T* grad_bar, T* local, void* stream);    \
+  int tfem_interp_edges_bwd_##SUF(int64_t n_edge, int64_t n_edge_per_mesh, int64_t n_el_per_mesh,  \
+                                  const int32_t* edge_cells, const T* first_vertex,                \
+                                  const T* inv_jac, int d, const T* x_q, int n_q,                  \
+                                  const T* val_bar, const T* grad_bar, T* local, void* stream);    \
   /* Jump estimator eta_E = sum_q dx h_E (grad u+ . n - grad u- . n)^2                            \
    * (examples/example_jump.py:75-87 integrated by basis/abstract_basis.py:65-72).              \
    * grad_edges [n_edge,2,d] from tfem_interp_edges, normals [n_edge,d], h_e [n_edge],           \

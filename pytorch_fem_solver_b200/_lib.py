@@ -73,6 +73,8 @@ _TYPED = {
     "tfem_weak_residual_bwd": [I64, I64, I64, P, P, P, c_int, P, P, P, P, P, P],
     "tfem_interp_cells": [I64, P, P, c_int, c_int, P, P, P, P],
     "tfem_interp_edges": [I64, I64, I64, P, P, P, P, c_int, P, c_int, P, P, P, P],
+    "tfem_interp_cells_bwd": [I64, P, c_int, c_int, P, P, P, P],
+    "tfem_interp_edges_bwd": [I64, I64, I64, P, P, P, c_int, P, c_int, P, P, P, P],
     "tfem_edge_jump": [I64, c_int, c_int, P, P, P, P, P, P],
     "tfem_iface_pack": [I64, P, P, P, P],
     "tfem_iface_unpack_add": [I64, P, P, P, P],

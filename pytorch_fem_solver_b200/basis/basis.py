@@ -57,19 +57,36 @@ class Basis(AbstractBasis):
         x_q = basis.integration_points.reshape(-1, basis.n_q, 2).contiguous()
         return cells, lay.conn, first, inv, x_q, cells.shape[0], lay.n_el_per_mesh
 
+    def _edge_scatter_maps(self, basis, cells, conn, n_edge_per_mesh, n_el_per_mesh):
+        """(seg, perm, inverse) of the (edge, side, local vertex) -> DOF relation: adjoint of edge interpolation."""
+        key = ("edge_maps", id(basis))
+        if key not in self._scatter_inverse:
+            n_edge = cells.shape[0]
+            mesh_of_edge = torch.arange(n_edge, device=cells.device) // n_edge_per_mesh
+            global_cell = (mesh_of_edge[:, None] * n_el_per_mesh + cells.long()).reshape(-1)
+            dof = conn.long()[global_cell].reshape(-1)  # (2E*3,)
+            n_dof = self.n_dof_flat
+            order = torch.argsort(dof, stable=True)
+            seg = torch.zeros(n_dof + 1, dtype=torch.int64, device=cells.device)
+            seg[1:] = torch.cumsum(torch.bincount(dof, minlength=n_dof), 0)
+            self._scatter_inverse[key] = (seg.to(torch.int32), order.to(torch.int32), dof.to(torch.int32).contiguous())
+        return self._scatter_inverse[key]
+
     def _interpolate_values(self, basis, nodal: torch.Tensor):
-        if nodal.requires_grad:
-            raise NotImplementedError(
-                "differentiating through Basis.interpolate is not implemented yet; pass detached nodal values"
-            )
         u = nodal.to(self.dtype).reshape(-1).contiguous()
+        needs_grad = u.requires_grad
         if basis is self:
+            maps = (None, None, None)
+            if needs_grad:
+                pat = self.pattern
+                maps = (pat.lin_seg, pat.lin_perm, self._inverse("linear"))
             val, grad = ops.interp_cells(u, self._dof_conn_flat(), self.v_grad.reshape(-1, 3, self._layout.d).contiguous(),
-                                         self._element.integration_order)
+                                         self._element.integration_order, *maps)
             lead = self._layout.lead
             return val.reshape(*lead, self.n_q, 1, 1), grad.reshape(*lead, 1, 1, self._layout.d)
         cells, conn, first, inv, x_q, n_edge_per_mesh, n_el_per_mesh = self._edge_interpolation_inputs(basis)
-        val, grad = ops.interp_edges(u, cells, conn, first, inv, x_q, n_edge_per_mesh, n_el_per_mesh)
+        maps = self._edge_scatter_maps(basis, cells, conn, n_edge_per_mesh, n_el_per_mesh) if needs_grad else (None, None, None)
+        val, grad = ops.interp_edges(u, cells, conn, first, inv, x_q, n_edge_per_mesh, n_el_per_mesh, *maps)
         lead = basis._layout.lead
         d = x_q.shape[-1]
         return val.reshape(*lead, 2, basis.n_q, 1, 1), grad.reshape(*lead, 2, 1, 1, d)

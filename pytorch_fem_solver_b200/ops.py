@@ -419,8 +419,14 @@ weak_residual.register_autograd(_weak_residual_backward, setup_context=_weak_res
 
 
 @torch.library.custom_op(f"{NS}::interp_cells", mutates_args=())
-def interp_cells(u: Tensor, dof_conn: Tensor, v_grad: Tensor, quad_order: int) -> Tuple[Tensor, Tensor]:
-    """u (n_dof,), dof_conn (N,3), v_grad (N,3,d) -> values (N,q), gradients (N,d)."""
+def interp_cells(
+    u: Tensor, dof_conn: Tensor, v_grad: Tensor, quad_order: int, seg: Optional[Tensor] = None,
+    perm: Optional[Tensor] = None, inverse: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor]:
+    """u (n_dof,), dof_conn (N,3), v_grad (N,3,d) -> values (N,q), gradients (N,d).
+
+    `seg`/`perm`/`inverse` (the linear-form scatter maps of the basis) are only needed to
+    differentiate w.r.t. `u`."""
     device = check_cuda(u, dof_conn, v_grad)
     n_q = _nq_tri(quad_order)
     n_el, _, d = v_grad.shape
@@ -431,8 +437,42 @@ def interp_cells(u: Tensor, dof_conn: Tensor, v_grad: Tensor, quad_order: int) -
 
 
 @interp_cells.register_fake
-def _(u, dof_conn, v_grad, quad_order):
+def _(u, dof_conn, v_grad, quad_order, seg=None, perm=None, inverse=None):
     return u.new_empty((v_grad.shape[0], TRI_NQ[quad_order])), u.new_empty((v_grad.shape[0], v_grad.shape[2]))
+
+
+@torch.library.custom_op(f"{NS}::interp_cells_bwd", mutates_args=())
+def interp_cells_bwd(val_bar: Tensor, grad_bar: Tensor, v_grad: Tensor, quad_order: int) -> Tensor:
+    """Per-element part (N,3) of the adjoint of `interp_cells` w.r.t. u."""
+    device = check_cuda(val_bar, grad_bar, v_grad)
+    n_el, _, d = v_grad.shape
+    local = torch.empty((n_el, 3), dtype=v_grad.dtype, device=device)
+    call("tfem_interp_cells_bwd", v_grad.dtype, device, n_el, ptr(v_grad), d, quad_order, ptr(val_bar), ptr(grad_bar), ptr(local))
+    return local
+
+
+@interp_cells_bwd.register_fake
+def _(val_bar, grad_bar, v_grad, quad_order):
+    return v_grad.new_empty((v_grad.shape[0], 3))
+
+
+def _interp_cells_setup(ctx, inputs, output):
+    u, dof_conn, v_grad, quad_order, seg, perm, inverse = inputs
+    ctx.save_for_backward(v_grad, seg, perm, inverse)
+    ctx.quad_order = quad_order
+    ctx.n_dof = u.shape[0]
+
+
+def _interp_cells_backward(ctx, val_bar, grad_bar):
+    v_grad, seg, perm, inverse = ctx.saved_tensors
+    if seg is None:
+        raise TfemError("differentiating interp_cells w.r.t. u needs the scatter maps (seg, perm, inverse)")
+    local = interp_cells_bwd(val_bar.contiguous(), grad_bar.contiguous(), v_grad, ctx.quad_order)
+    u_bar = scatter(local.reshape(-1), seg, perm, inverse)
+    return u_bar, None, None, None, None, None, None
+
+
+interp_cells.register_autograd(_interp_cells_backward, setup_context=_interp_cells_setup)
 
 
 @torch.library.custom_op(f"{NS}::interp_edges", mutates_args=())
@@ -445,8 +485,14 @@ def interp_edges(
     x_q: Tensor,
     n_edge_per_mesh: int,
     n_el_per_mesh: int,
+    seg: Optional[Tensor] = None,
+    perm: Optional[Tensor] = None,
+    inverse: Optional[Tensor] = None,
 ) -> Tuple[Tensor, Tensor]:
-    """Both cells of every interior edge at the edge points: values (E,2,q), gradients (E,2,d)."""
+    """Both cells of every interior edge at the edge points: values (E,2,q), gradients (E,2,d).
+
+    `seg`/`perm`/`inverse` (scatter maps of the (edge, side, local vertex) -> DOF relation) are
+    only needed to differentiate w.r.t. `u`."""
     device = check_cuda(u, edge_cells, conn, first_vertex, inv_jac, x_q)
     n_edge, n_q, d = x_q.shape
     val = torch.empty((n_edge, 2, n_q), dtype=u.dtype, device=device)
@@ -459,9 +505,48 @@ def interp_edges(
 
 
 @interp_edges.register_fake
-def _(u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh):
+def _(u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh, seg=None, perm=None, inverse=None):
     n_edge, n_q, d = x_q.shape
     return u.new_empty((n_edge, 2, n_q)), u.new_empty((n_edge, 2, d))
+
+
+@torch.library.custom_op(f"{NS}::interp_edges_bwd", mutates_args=())
+def interp_edges_bwd(
+    val_bar: Tensor, grad_bar: Tensor, edge_cells: Tensor, first_vertex: Tensor, inv_jac: Tensor, x_q: Tensor,
+    n_edge_per_mesh: int, n_el_per_mesh: int,
+) -> Tensor:
+    """Per-(edge, side) part (2E,3) of the adjoint of `interp_edges` w.r.t. u."""
+    device = check_cuda(val_bar, grad_bar, edge_cells, first_vertex, inv_jac, x_q)
+    n_edge, n_q, d = x_q.shape
+    local = torch.empty((2 * n_edge, 3), dtype=x_q.dtype, device=device)
+    call(
+        "tfem_interp_edges_bwd", x_q.dtype, device, n_edge, n_edge_per_mesh, n_el_per_mesh, ptr(edge_cells),
+        ptr(first_vertex), ptr(inv_jac), d, ptr(x_q), n_q, ptr(val_bar), ptr(grad_bar), ptr(local),
+    )
+    return local
+
+
+@interp_edges_bwd.register_fake
+def _(val_bar, grad_bar, edge_cells, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh):
+    return x_q.new_empty((2 * x_q.shape[0], 3))
+
+
+def _interp_edges_setup(ctx, inputs, output):
+    u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh, seg, perm, inverse = inputs
+    ctx.save_for_backward(edge_cells, first_vertex, inv_jac, x_q, seg, perm, inverse)
+    ctx.sizes = (n_edge_per_mesh, n_el_per_mesh)
+
+
+def _interp_edges_backward(ctx, val_bar, grad_bar):
+    edge_cells, first_vertex, inv_jac, x_q, seg, perm, inverse = ctx.saved_tensors
+    if seg is None:
+        raise TfemError("differentiating interp_edges w.r.t. u needs the scatter maps (seg, perm, inverse)")
+    local = interp_edges_bwd(val_bar.contiguous(), grad_bar.contiguous(), edge_cells, first_vertex, inv_jac, x_q, *ctx.sizes)
+    u_bar = scatter(local.reshape(-1), seg, perm, inverse)
+    return (u_bar,) + (None,) * 10
+
+
+interp_edges.register_autograd(_interp_edges_backward, setup_context=_interp_edges_setup)
 
 
 @torch.library.custom_op(f"{NS}::edge_jump", mutates_args=())
@@ -477,6 +562,21 @@ def edge_jump(grad_edges: Tensor, normals: Tensor, h_e: Tensor, dx: Tensor) -> T
 @edge_jump.register_fake
 def _(grad_edges, normals, h_e, dx):
     return grad_edges.new_empty((grad_edges.shape[0],))
+
+
+def _edge_jump_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _edge_jump_backward(ctx, eta_bar):
+    # d eta / d grad(+/-) = +/- 2 h_E (sum_q dx) jump n : elementwise on (E,2,d), a few tiny torch ops
+    grad_edges, normals, h_e, dx = ctx.saved_tensors
+    jump = ((grad_edges[:, 0] - grad_edges[:, 1]) * normals).sum(-1)
+    coef = (2.0 * h_e * dx.sum(-1) * jump * eta_bar).unsqueeze(-1) * normals
+    return torch.stack([coef, -coef], dim=1), None, None, None
+
+
+edge_jump.register_autograd(_edge_jump_backward, setup_context=_edge_jump_setup)
 
 
 # ------------------------------------------------------------------------------------------------

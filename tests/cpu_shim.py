@@ -182,7 +182,7 @@ def weak_residual(grad_u, coords, conn, dof_conn, lin_seg, lin_perm, n_el_per_me
     return _WeakResidual.apply(grad_u, meta)
 
 
-def interp_cells(u, dof_conn, v_grad, quad_order):
+def interp_cells(u, dof_conn, v_grad, quad_order, seg=None, perm=None, inverse=None):
     nodes, _ = fo.tri_quadrature(quad_order)
     bar = fo.tri_barycentric(nodes)  # (q,3,1)
     nodal = _np(u)[_np(dof_conn).astype(np.int64)]  # (N,3)
@@ -191,7 +191,7 @@ def interp_cells(u, dof_conn, v_grad, quad_order):
     return torch.from_numpy(val).to(u.dtype), torch.from_numpy(grad).to(u.dtype)
 
 
-def interp_edges(u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh):
+def interp_edges(u, edge_cells, conn, first_vertex, inv_jac, x_q, n_edge_per_mesh, n_el_per_mesh, seg=None, perm=None, inverse=None):
     n_edge, n_q, d = x_q.shape
     n_mesh = n_edge // n_edge_per_mesh
     cells = _np(edge_cells).astype(np.int64).reshape(n_mesh, n_edge_per_mesh, 2)

@@ -250,3 +250,87 @@ def test_geometry_config2_roundtrip(config2):
     pts = basis.integration_points
     assert pts.shape == (4194304, 4, 1, 2)
     assert float(pts.min()) >= 0.0 and float(pts.max()) <= 1.0
+
+
+# ------------------------------------------------------------------ differentiable interpolation
+def _torch_interp_cells(basis, u):
+    """Plain torch restatement (differentiable) of Basis.interpolate(self, u)."""
+    conn = basis._dof_conn_flat().long()
+    local = u.reshape(-1)[conn]  # (N,3)
+    val = torch.einsum("ni,nqi->nq", local, basis.v.reshape(-1, basis.n_q, 3).expand(conn.shape[0], -1, -1))
+    grad = torch.einsum("ni,nic->nc", local, basis.v_grad.reshape(-1, 3, 2))
+    return val, grad
+
+
+def test_interpolate_cells_gradient_matches_torch_autograd():
+    mesh = meshgen.structured_rectangle(30, 18, jitter=0.2, seed=5, topology=False)
+    basis = make_basis(mesh, 3)
+    n = basis.n_dof_flat
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    u0 = torch.randn(n, 1, dtype=torch.float64, generator=gen).to(DEV)
+    wv = torch.randn(basis._layout.n_total, basis.n_q, dtype=torch.float64, generator=gen).to(DEV)
+    wg = torch.randn(basis._layout.n_total, 2, dtype=torch.float64, generator=gen).to(DEV)
+
+    u = u0.clone().requires_grad_(True)
+    val, grad = basis.interpolate(basis, u)
+    loss = (val.reshape(-1, basis.n_q) * wv).sum() + (grad.reshape(-1, 2) ** 2 * wg).sum()
+    (g_ours,) = torch.autograd.grad(loss, u)
+
+    u_ref = u0.clone().requires_grad_(True)
+    val_r, grad_r = _torch_interp_cells(basis, u_ref)
+    assert relmax(val.detach().reshape(-1).cpu().numpy(), val_r.detach().reshape(-1).cpu().numpy()) < 1e-13
+    loss_r = (val_r * wv).sum() + (grad_r**2 * wg).sum()
+    (g_ref,) = torch.autograd.grad(loss_r, u_ref)
+    assert relmax(g_ours.cpu().numpy(), g_ref.cpu().numpy()) < 1e-12
+
+    # deterministic adjoint: same bits twice
+    u2 = u0.clone().requires_grad_(True)
+    val2, grad2 = basis.interpolate(basis, u2)
+    (g_again,) = torch.autograd.grad((val2.reshape(-1, basis.n_q) * wv).sum() + (grad2.reshape(-1, 2) ** 2 * wg).sum(), u2)
+    assert torch.equal(g_ours, g_again)
+
+
+def test_jump_estimator_gradient_matches_torch_autograd():
+    """d(sum eta_E)/du through interpolate(edges) + the fused jump kernel (example_jump.py:75-87)."""
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        with torch.device(DEV):
+            mesh = tfem.MeshTri(meshgen.structured_rectangle(14, 11, jitter=0.2, seed=9))
+            basis = tfem.Basis(mesh, tfem.ElementTri(1, 2))
+            edges = tfem.InteriorEdgesBasis(mesh, tfem.ElementLine(1, 2))
+    finally:
+        torch.set_default_dtype(previous)
+    n = basis.n_dof_flat
+    gen = torch.Generator(device="cpu").manual_seed(2)
+    u0 = torch.randn(n, 1, dtype=torch.float64, generator=gen).to(DEV)
+    h_e = mesh["interior_edges", "length"].unsqueeze(-2)
+    n_e = mesh["interior_edges", "normals"].unsqueeze(-2)
+
+    u = u0.clone().requires_grad_(True)
+    val, grad = basis.interpolate(edges, u)
+    eta = edges.integrate_functional(forms.Jump(grad), n_e, h_e)
+    weights = torch.linspace(0.5, 1.5, eta.numel(), dtype=torch.float64, device=DEV).reshape(eta.shape)
+    (g_ours,) = torch.autograd.grad((eta * weights).sum() + 0.1 * (val**2).sum(), u)
+
+    # torch restatement: gather the two cells of each edge and apply the same formulas
+    cells = mesh["interior_edges", "cells"].reshape(-1, 2).long()
+    conn = basis._dof_conn_flat().long()
+    u_ref = u0.clone().requires_grad_(True)
+    local = u_ref.reshape(-1)[conn[cells]]  # (E,2,3)
+    inv = basis._inv_map_jacobian.reshape(-1, 2, 2)[cells]  # (E,2,2,2)
+    first = mesh["cells", "coordinates"][..., 0, :].reshape(-1, 2)[cells]  # (E,2,2)
+    x_q = edges.integration_points.reshape(-1, edges.n_q, 2)
+    ref_pts = torch.einsum("esqc,esrc->esqr", x_q[:, None] - first[:, :, None], inv)  # (E,2,q,2)
+    lam = torch.stack([1 - ref_pts[..., 0] - ref_pts[..., 1], ref_pts[..., 0], ref_pts[..., 1]], -1)  # (E,2,q,3)
+    val_r = torch.einsum("esi,esqi->esq", local, lam)
+    ghat = torch.tensor([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]], dtype=torch.float64, device=DEV)
+    grad_r = torch.einsum("esi,ir,esrc->esc", local, ghat, inv)
+    assert relmax(val.detach().reshape(-1).cpu().numpy(), val_r.detach().reshape(-1).cpu().numpy()) < 1e-12
+    assert relmax(grad.detach().reshape(-1).cpu().numpy(), grad_r.detach().reshape(-1).cpu().numpy()) < 1e-12
+    normal = n_e.reshape(-1, 2)
+    jump = ((grad_r[:, 0] - grad_r[:, 1]) * normal).sum(-1)
+    eta_r = h_e.reshape(-1) * jump**2 * edges._dx.reshape(-1, edges.n_q).sum(-1)
+    assert relmax(eta.detach().reshape(-1).cpu().numpy(), eta_r.detach().cpu().numpy()) < 1e-12
+    (g_ref,) = torch.autograd.grad((eta_r * weights.reshape(-1)).sum() + 0.1 * (val_r**2).sum(), u_ref)
+    assert relmax(g_ours.cpu().numpy(), g_ref.cpu().numpy()) < 1e-12
