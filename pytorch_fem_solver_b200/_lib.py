@@ -47,12 +47,15 @@ class TilePlan(Structure):
         ("tile_list", c_void_p),
         ("e_off", c_void_p),
         ("e_blob", c_void_p),
-        ("l_off", c_void_p),
-        ("l_blob", c_void_p),
+        ("la_off", c_void_p),
+        ("la_blob", c_void_p),
+        ("lb_off", c_void_p),
+        ("lb_blob", c_void_p),
         ("max_vert", c_int32),
         ("max_elem", c_int32),
         ("max_e_words", c_int32),
-        ("max_l_words", c_int32),
+        ("max_la_words", c_int32),
+        ("max_lb_words", c_int32),
         ("consumer_threads", c_int32),
         ("elem_stride", c_int32),
         ("reserve_ctas", c_int32),

@@ -1,13 +1,15 @@
 """Row-tile plan of the fused assembly kernel (`tfem_tri_p1_assemble_csr`).
 
 Integer, one-time set-up in torch (any device).  CSR rows are clustered into tiles; for every tile
-two packed, 16 B-aligned blobs are produced (layouts in include/tfem_b200.h):
+three packed, 16 B-aligned blobs are produced (layouts in include/tfem_b200.h):
 
   E ("early")  what the producer warp and the integration phase need: header, the tile's
                vertices (rows of `coords`) and its tile-local connectivity;
-  L ("late")   what the reduction phase needs: owned row ids, runs of consecutive rows, and for
-               every CSR entry of the tile the list of (element, local-matrix slot) contributions
-               in increasing element order, likewise for the load entries.
+  LA ("late", entries)  segments of consecutive CSR slots and for every CSR entry of the tile ONE
+               word holding its (at most two) contributions as (local-matrix slot, element)
+               codes in increasing element order;
+  LB ("late", rows)  owned row ids and for every row fixed-size chunks listing the elements of
+               its load / diagonal entry.
 
 Each blob is fetched by one TMA bulk copy, so per-tile sections are padded to whole 16 B units.
 """
@@ -122,13 +124,16 @@ class TilePlan:
     n_tiles: int
     e_off: torch.Tensor
     e_blob: torch.Tensor
-    l_off: torch.Tensor
-    l_blob: torch.Tensor
+    la_off: torch.Tensor
+    la_blob: torch.Tensor
+    lb_off: torch.Tensor
+    lb_blob: torch.Tensor
     max_vert: int
     max_elem: int
     elem_stride: int  # row length of the shared local-matrix table; contribution codes index it directly
     max_e_words: int
-    max_l_words: int
+    max_la_words: int
+    max_lb_words: int
     max_rows: int
     max_out: int
     halo_factor: float  # tile elements / mesh elements (1.0 = every element integrated once)
@@ -143,8 +148,10 @@ class TilePlan:
         s.n_tiles = self.n_tiles if self.tile_list is None else int(self.tile_list.numel())
         s.tile_list = None if self.tile_list is None else self.tile_list.data_ptr()
         s.e_off, s.e_blob = self.e_off.data_ptr(), self.e_blob.data_ptr()
-        s.l_off, s.l_blob = self.l_off.data_ptr(), self.l_blob.data_ptr()
-        s.max_vert, s.max_elem, s.max_e_words, s.max_l_words = self.max_vert, self.max_elem, self.max_e_words, self.max_l_words
+        s.la_off, s.la_blob = self.la_off.data_ptr(), self.la_blob.data_ptr()
+        s.lb_off, s.lb_blob = self.lb_off.data_ptr(), self.lb_blob.data_ptr()
+        s.max_vert, s.max_elem, s.max_e_words = self.max_vert, self.max_elem, self.max_e_words
+        s.max_la_words, s.max_lb_words = self.max_la_words, self.max_lb_words
         s.elem_stride = self.elem_stride
         s.reserve_ctas = self.reserve_ctas
         s.consumer_threads = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads))
@@ -177,26 +184,30 @@ class TilePlan:
             return vals, pos + ((n_words + 3) & ~3)
 
         e = words_of(self.e_off, self.e_blob)
-        names = ("n_vert", "n_elem", "n_rows", "n_runs", "n_out", "n_contrib", "base_vertex", "n_lcontrib", "n_heavy")
+        names = ("n_vert", "n_elem", "n_rows", "n_runs", "n_out", "n_chunks", "base_vertex", "n_heavy_contrib", "n_heavy")
         out = {k: int(v) for k, v in zip(names, e[:HEADER_WORDS])}
         pos = HEADER_WORDS
         out["vert"], pos = unpack(e, pos, out["n_vert"], 32)
         out["elem"], pos = unpack(e, pos, out["n_elem"], 32)
-        lw = words_of(self.l_off, self.l_blob)
-        pos = 0
-        for name, n, bits in (
-            ("row_id", out["n_rows"], 32),
-            ("run_start", out["n_runs"], 32),
-            ("run_meta", out["n_runs"], 32),
-            ("ent_seg", out["n_out"] + 1, 16),
-            ("contrib", out["n_contrib"], 16),
-            ("lrow_seg", out["n_rows"] + 1, 16),
-            ("lcontrib", out["n_lcontrib"], 16),
-            ("row_diag", out["n_rows"], 32),
-            ("heavy", out["n_heavy"], 16),
-            ("heavy_pos", out["n_heavy"], 32),
+        for off, blob, layout in (
+            (self.la_off, self.la_blob, (
+                ("run_start", out["n_runs"], 32),
+                ("run_meta", out["n_runs"], 32),
+                ("pair", out["n_out"], 32),
+                ("heavy_seg", out["n_heavy"] + 1, 16),
+                ("heavy_contrib", out["n_heavy_contrib"], 16),
+                ("heavy_pos", out["n_heavy"], 32),
+            )),
+            (self.lb_off, self.lb_blob, (
+                ("row_id", out["n_rows"], 32),
+                ("row_chunk", 8 * out["n_chunks"], 16),
+                ("row_diag", out["n_rows"], 32),
+            )),
         ):
-            out[name], pos = unpack(lw, pos, n, bits)
+            lw = words_of(off, blob)
+            pos = 0
+            for name, n, bits in layout:
+                out[name], pos = unpack(lw, pos, n, bits)
         return out
 
 
@@ -284,17 +295,24 @@ def build_tile_plan(
     new_run = torch.ones(n_dof, dtype=torch.bool, device=device)
     if n_dof > 1:
         new_run[1:] = (row_tile[1:] != row_tile[:-1]) | (row_sorted[1:] != row_sorted[:-1] + 1)
-    run_of_row = torch.cumsum(new_run.long(), 0) - 1
     run_first = torch.nonzero(new_run, as_tuple=True)[0]
     run_last = torch.cat([run_first[1:], torch.tensor([n_dof], device=device)]) - 1
-    run_tile = row_tile[run_first]
+    whole_start = crow[row_sorted[run_first]]
+    whole_len = crow[row_sorted[run_last] + 1] - whole_start
+    whole_base = row_out[run_first] - tile_out0[row_tile[run_first]]
+    # ... cut into segments of at most 32 entries: one warp, one lane per entry, no inner loop
+    SEG = 32
+    pieces = torch.div(whole_len + SEG - 1, SEG, rounding_mode="floor")
+    piece_run = torch.repeat_interleave(arange(whole_len.numel()), pieces)
+    piece_k = arange(piece_run.numel()) - _excl_cumsum(pieces)[piece_run]
+    run_tile = row_tile[run_first][piece_run]
     run_ptr = _ptr(run_tile, n_tiles)
     n_u = run_ptr[1:] - run_ptr[:-1]
-    run_start = crow[row_sorted[run_first]]
-    run_len = crow[row_sorted[run_last] + 1] - run_start
-    run_base = row_out[run_first] - tile_out0[run_tile]
-    if int(n_out.max().item()) > 65535 or int(n_u.max().item()) > 255:
-        raise ValueError("tile image too large (entries > 65535 or runs > 255): lower rows_per_tile")
+    run_start = whole_start[piece_run] + SEG * piece_k
+    run_len = (whole_len[piece_run] - SEG * piece_k).clamp_max(SEG)
+    run_base = whole_base[piece_run] + SEG * piece_k
+    if int(n_out.max().item()) > 65535 or int(n_u.max().item()) > 65535:
+        raise ValueError("tile image too large (entries or segments > 65535): lower rows_per_tile")
 
     # 5. every CSR entry of a tile with its contributions (element ascending = reference order)
     nnz = pattern.nnz
@@ -305,8 +323,6 @@ def build_tile_plan(
     seg = pattern.seg.long()
     ent_cnt = seg[ent_global + 1] - seg[ent_global]
     ent_coff = _excl_cumsum(ent_cnt)
-    n_c = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, ent_tile, ent_cnt)
-    tile_c0 = _excl_cumsum(n_c)
     total_c = int(ent_cnt.sum().item())
     c_ent = torch.repeat_interleave(arange(nnz), ent_cnt)
     c_within = arange(total_c) - ent_coff[c_ent]
@@ -316,42 +332,33 @@ def build_tile_plan(
     c_j = coo - 9 * c_e - 3 * c_i
     slot = torch.where(c_i == c_j, c_i, 3 + (c_i + c_j == 3).long() + 2 * (c_i + c_j == 2).long())  # K00 K11 K22 K01 K12 K20
     c_tile = ent_tile[c_ent]
-    elem_stride = (max_elem + 31) & ~31  # sloc is [9][elem_stride]; codes below index it directly
+    # sloc is [9][elem_stride]; codes `slot*elem_stride + element` index it directly.  The last
+    # column (element elem_stride-1) is never written by the integration phase and holds zeros:
+    # `zero_code` pads every fixed-length contribution list.
+    elem_stride = (max_elem + 1 + 31) & ~31
+    zero_code = elem_stride - 1
     if 9 * elem_stride > 65535:
         raise ValueError("tile has too many elements for 16-bit local-matrix indices: lower rows_per_tile")
     c_code = (torch.searchsorted(pair_keys, c_tile * n_el + c_e) - elem_ptr[c_tile]) + slot * elem_stride
-    # per-tile entry offsets, n_out+1 values each
-    seg_tile = torch.repeat_interleave(tiles, n_out + 1)
-    seg_local = arange(seg_tile.numel()) - (_excl_cumsum(n_out) + tiles)[seg_tile]
-    seg_global_slot = tile_out0[seg_tile] + seg_local  # slot index into the tile-ordered image, may equal nnz
-    ent_coff_ext = torch.cat([ent_coff, torch.tensor([total_c], device=device)])
-    seg_value = ent_coff_ext[seg_global_slot] - tile_c0[seg_tile]
-    if int(n_c.max().item()) > 65535:
-        raise ValueError("tile has more than 65535 contributions: lower rows_per_tile")
 
     # 6. load-vector contributions per owned row
     lseg = pattern.lin_seg.long()
     lrow_cnt = lseg[row_sorted + 1] - lseg[row_sorted]
     lrow_off = _excl_cumsum(lrow_cnt)
-    n_lc = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, row_tile, lrow_cnt)
-    tile_lc0 = _excl_cumsum(n_lc)
     total_lc = int(lrow_cnt.sum().item())
     lc_row = torch.repeat_interleave(arange(n_dof), lrow_cnt)
-    lc_flat = pattern.lin_perm.long()[lseg[row_sorted[lc_row]] + (arange(total_lc) - lrow_off[lc_row])]
+    lc_within = arange(total_lc) - lrow_off[lc_row]
+    lc_flat = pattern.lin_perm.long()[lseg[row_sorted[lc_row]] + lc_within]
     lc_e = torch.div(lc_flat, 3, rounding_mode="floor")
     lc_k = lc_flat - 3 * lc_e
     lc_tile = row_tile[lc_row]
     lc_code = (torch.searchsorted(pair_keys, lc_tile * n_el + lc_e) - elem_ptr[lc_tile]) + lc_k * elem_stride
-    lseg_tile = torch.repeat_interleave(tiles, n_r + 1)
-    lseg_local = arange(lseg_tile.numel()) - (row_ptr[:-1] + tiles)[lseg_tile]
-    lrow_off_ext = torch.cat([lrow_off, torch.tensor([total_lc], device=device)])
-    lseg_value = lrow_off_ext[row_ptr[lseg_tile] + lseg_local] - tile_lc0[lseg_tile]
 
     # 6b. who sums which entry.  One thread per entry handles entries with <= 2 contributions
-    #     (every off-diagonal entry of a manifold mesh) without a loop; the diagonal of a row is
-    #     summed by the row's thread together with its load entry (same element list); anything
-    #     else with > 2 contributions (non-manifold edges, degenerate elements) goes to a short
-    #     "heavy" list handled by a generic loop.
+    #     (every off-diagonal entry of a manifold mesh) from ONE packed word, without a loop; the
+    #     diagonal of a row is summed by the row's thread together with its load entry (same element
+    #     list); anything else with > 2 contributions (non-manifold edges, degenerate elements)
+    #     goes to a short "heavy" list handled by a generic loop.
     ent_is_diag = pattern.col.long()[ent_global] == row_sorted[ent_row]
     off_slot = torch.zeros(nnz, dtype=torch.int64, device=device).index_add_(0, c_ent, (slot >= 3).long())
     diag_fast = ent_is_diag & (ent_cnt > 2) & (off_slot == 0) & (ent_cnt == lrow_cnt[ent_row])
@@ -361,9 +368,64 @@ def build_tile_plan(
     heavy_tile = ent_tile[heavy]
     n_h = torch.bincount(heavy_tile, minlength=n_tiles)
     heavy_local = arange(heavy_tile.numel()) - _excl_cumsum(n_h)[heavy_tile]
+    # contributions of the heavy entries, with per-tile offsets (n_h + 1 values per tile)
+    heavy_ids = torch.nonzero(heavy, as_tuple=True)[0]
+    heavy_cnt = ent_cnt[heavy_ids]
+    n_hc = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, heavy_tile, heavy_cnt)
+    heavy_coff = _excl_cumsum(heavy_cnt)
+    total_hc = int(heavy_cnt.sum().item())
+    if int(n_hc.max().item()) > 65535:
+        raise ValueError("tile has more than 65535 heavy contributions: lower rows_per_tile")
+    hc_item = torch.repeat_interleave(arange(heavy_ids.numel()), heavy_cnt)
+    hc_code = c_code[ent_coff[heavy_ids[hc_item]] + (arange(total_hc) - heavy_coff[hc_item])]
+    hc_tile = heavy_tile[hc_item]
+    tile_hc0 = _excl_cumsum(n_hc)
+    hseg_tile = torch.repeat_interleave(tiles, n_h + 1)
+    hseg_local = arange(hseg_tile.numel()) - (_excl_cumsum(n_h) + tiles)[hseg_tile]
+    heavy_coff_ext = torch.cat([heavy_coff, torch.tensor([total_hc], device=device)])
+    hseg_value = heavy_coff_ext[_excl_cumsum(n_h)[hseg_tile] + hseg_local] - tile_hc0[hseg_tile]
+
+    # 6c. the packed pair of every entry: lo 16 bits = first contribution, hi 16 = second (zero_code
+    #     when absent); 0xFFFFFFFF = "not mine" (diagonal done by the row thread, or heavy)
+    first = torch.full((nnz,), zero_code, dtype=torch.int64, device=device)
+    second = torch.full((nnz,), zero_code, dtype=torch.int64, device=device)
+    first[c_ent[c_within == 0]] = c_code[c_within == 0]
+    second[c_ent[c_within == 1]] = c_code[c_within == 1]
+    pair = first | (second << 16)
+    pair[ent_cnt > 2] = 0xFFFFFFFF
+
+    # 6d. per-row chunks of 8 x u16: 7 contribution codes (k*elem_stride + element; zero_code pads)
+    #     and the tile-local index of the row's next chunk (0 = none).  Chunk j < n_rows is the first
+    #     chunk of row j; rows with more than 7 elements continue in chunks appended after n_rows.
+    PER = 7
+    row_chunks = torch.div(lrow_cnt + PER - 1, PER, rounding_mode="floor").clamp_min(1)
+    row_extra = row_chunks - 1
+    extra_off = _excl_cumsum(row_extra)
+    extra_in_tile = extra_off - extra_off[row_ptr[:-1].clamp_max(max(n_dof - 1, 0))][row_tile]
+    n_x = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, row_tile, row_extra)
+    n_ch = n_r + n_x
+    if int(n_ch.max().item()) > 65535:
+        raise ValueError("tile has more than 65535 row chunks: lower rows_per_tile")
+    chunk0 = _excl_cumsum(n_ch)
+    total_ch = int(n_ch.sum().item())
+    chunks = torch.full((total_ch, 8), zero_code, dtype=torch.int64, device=device)
+    chunks[:, 7] = 0
+    row_local = arange(n_dof) - row_ptr[row_tile]
+    lc_q = torch.div(lc_within, PER, rounding_mode="floor")
+    lc_chunk_local = torch.where(lc_q == 0, row_local[lc_row], n_r[lc_tile] + extra_in_tile[lc_row] + lc_q - 1)
+    chunks[chunk0[lc_tile] + lc_chunk_local, lc_within - PER * lc_q] = lc_code
+    # links: chunk q of a row -> chunk q+1
+    link_row = torch.repeat_interleave(arange(n_dof), row_extra)
+    link_q = arange(link_row.numel()) - extra_off[link_row]  # 0-based: link from chunk q to q+1
+    link_tile = row_tile[link_row]
+    link_to = n_r[link_tile] + extra_in_tile[link_row] + link_q
+    link_from = torch.where(link_q == 0, row_local[link_row], link_to - 1)
+    chunks[chunk0[link_tile] + link_from, 7] = link_to
+    chunk_tile = torch.repeat_interleave(tiles, n_ch * 8)
+    chunk_local = arange(total_ch * 8) - (chunk0 * 8)[chunk_tile]
 
     # 7. pack
-    header = torch.stack([n_v, n_e, n_r, n_u, n_out, n_c, base_vertex, n_lc, n_h, n_h * 0, n_h * 0, n_h * 0], dim=1).reshape(-1)
+    header = torch.stack([n_v, n_e, n_r, n_u, n_out, n_ch, base_vertex, n_hc, n_h, n_h * 0, n_h * 0, n_h * 0], dim=1).reshape(-1)
     hdr_tile = torch.repeat_interleave(tiles, HEADER_WORDS)
     hdr_local = arange(hdr_tile.numel()) % HEADER_WORDS
     e_sections = [
@@ -371,36 +433,40 @@ def build_tile_plan(
         _Section("vert", 32, n_v, vert_tile, arange(vert_tile.numel()) - vert_ptr[vert_tile], tile_vert),
         _Section("elem", 32, n_e, pair_tile, arange(pair_tile.numel()) - elem_ptr[pair_tile], tile_elem),
     ]
-    row_local = arange(n_dof) - row_ptr[row_tile]
     run_local = arange(run_tile.numel()) - run_ptr[run_tile]
-    l_sections = [
-        _Section("row_id", 32, n_r, row_tile, row_local, row_sorted),
+    la_sections = [
         _Section("run_start", 32, n_u, run_tile, run_local, run_start),
         _Section("run_meta", 32, n_u, run_tile, run_local, run_base | (run_len << 16)),
-        _Section("ent_seg", 16, n_out + 1, seg_tile, seg_local, seg_value),
-        _Section("contrib", 16, n_c, c_tile, arange(total_c) - tile_c0[c_tile], c_code),
-        _Section("lrow_seg", 16, n_r + 1, lseg_tile, lseg_local, lseg_value),
-        _Section("lcontrib", 16, n_lc, lc_tile, arange(total_lc) - tile_lc0[lc_tile], lc_code),
-        _Section("row_diag", 32, n_r, row_tile, row_local, row_diag),
-        _Section("heavy", 16, n_h, heavy_tile, heavy_local, ent_local[heavy]),
+        _Section("pair", 32, n_out, ent_tile, ent_local, pair),
+        _Section("heavy_seg", 16, n_h + 1, hseg_tile, hseg_local, hseg_value),
+        _Section("heavy_contrib", 16, n_hc, hc_tile, arange(total_hc) - tile_hc0[hc_tile], hc_code),
         _Section("heavy_pos", 32, n_h, heavy_tile, heavy_local, ent_global[heavy]),
     ]
+    lb_sections = [
+        _Section("row_id", 32, n_r, row_tile, row_local, row_sorted),
+        _Section("row_chunk", 16, n_ch * 8, chunk_tile, chunk_local, chunks.reshape(-1)),
+        _Section("row_diag", 32, n_r, row_tile, row_local, row_diag),
+    ]
     e_off, e_blob, e_words = _pack(e_sections, n_tiles, device)
-    l_off, l_blob, l_words = _pack(l_sections, n_tiles, device)
+    la_off, la_blob, la_words = _pack(la_sections, n_tiles, device)
+    lb_off, lb_blob, lb_words = _pack(lb_sections, n_tiles, device)
     return TilePlan(
         n_tiles=n_tiles,
         e_off=e_off,
         e_blob=e_blob,
-        l_off=l_off,
-        l_blob=l_blob,
+        la_off=la_off,
+        la_blob=la_blob,
+        lb_off=lb_off,
+        lb_blob=lb_blob,
         max_vert=max_vert,
         max_elem=max_elem,
         elem_stride=elem_stride,
         max_e_words=int(e_words.max().item()),
-        max_l_words=int(l_words.max().item()),
+        max_la_words=int(la_words.max().item()),
+        max_lb_words=int(lb_words.max().item()),
         max_rows=int(n_r.max().item()),
         max_out=int(n_out.max().item()),
         halo_factor=float(pair_keys.shape[0]) / max(n_el, 1),
-        index_bytes=4 * (e_blob.numel() + l_blob.numel() + e_off.numel() + l_off.numel()),
+        index_bytes=4 * (e_blob.numel() + la_blob.numel() + lb_blob.numel() + e_off.numel() + la_off.numel() + lb_off.numel()),
         tile_of_row=tile_of_row,
     )

@@ -12,7 +12,7 @@ def emulate_tiled(plan, coords, local_mat, local_vec, geom_conn, nnz, n_dof):
 
     The emulator recovers each tile element's global id by matching tile-local vertices, so
     it also checks the vertex / connectivity sections for consistency."""
-    for off in (plan.e_off, plan.l_off):
+    for off in (plan.e_off, plan.la_off, plan.lb_off):
         assert np.all(off.cpu().numpy() % 4 == 0), "blobs must start on 16 B boundaries (TMA bulk copy)"
     elem_of = {tuple(v): e for e, v in enumerate(np.asarray(geom_conn).reshape(-1, 3).tolist())}
     csr_val = np.full(nnz, np.nan)
@@ -31,24 +31,22 @@ def emulate_tiled(plan, coords, local_mat, local_vec, geom_conn, nnz, n_dof):
             ge = elem_of[(verts[a], verts[b], verts[c])]
             m = local_mat[ge]
             sloc[:, el] = [m[0, 0], m[1, 1], m[2, 2], m[0, 1], m[1, 2], m[2, 0], *local_vec[ge]]
-        # phase C: one thread per CSR entry sums its contributions left to right
-        seg, contrib = sec["ent_seg"], sec["contrib"]
-        assert seg[0] == 0 and seg[-1] == sec["n_contrib"]
+        # phase C: one thread per CSR entry adds the (at most two) contributions packed in its word
         stride = plan.elem_stride
-        assert stride >= n_elem
+        assert stride > n_elem, "the last column of the local-matrix table must stay free (zeros)"
+        table = np.zeros((9, stride))
+        table[:, :n_elem] = sloc
+        zero_code = stride - 1
 
         def store(position, value):
             assert np.isnan(csr_val[position]), "every CSR entry is written exactly once"
             csr_val[position] = value
 
-        def entry_sum(o):
-            acc, previous = 0.0, -1
-            for code in contrib[seg[o] : seg[o + 1]]:
-                slot, el = divmod(int(code), stride)
-                assert slot < 6 and el >= previous, "contributions must come in increasing element order"
-                previous = el
-                acc += sloc[slot, el]
-            return acc
+        def lookup(code, previous):
+            slot, el = divmod(int(code), stride)
+            if code != zero_code:
+                assert slot < 6 and previous <= el < n_elem, "contributions must come in increasing element order"
+            return table[slot, el], el
 
         end = 0
         for start, meta in zip(sec["run_start"], sec["run_meta"]):  # light entries, run by run
@@ -56,21 +54,40 @@ def emulate_tiled(plan, coords, local_mat, local_vec, geom_conn, nnz, n_dof):
             assert base == end, "runs must tile the image in order"
             end = base + length
             for i in range(length):
-                if seg[base + i + 1] - seg[base + i] <= 2:
-                    store(start + i, entry_sum(base + i))
+                word = int(sec["pair"][base + i])
+                if word != 0xFFFFFFFF:
+                    first, el = lookup(word & 0xFFFF, -1)
+                    second, _ = lookup(word >> 16, el if (word & 0xFFFF) != zero_code else -1)
+                    store(start + i, first + second)
         assert end == sec["n_out"]
-        for o, position in zip(sec["heavy"], sec["heavy_pos"]):  # generic loop
-            assert seg[o + 1] - seg[o] > 2
-            store(position, entry_sum(o))
-        lseg = sec["lrow_seg"]
+        hseg = sec["heavy_seg"]
+        assert hseg[0] == 0 and hseg[-1] == sec["n_heavy_contrib"]
+        for h, position in enumerate(sec["heavy_pos"]):  # generic loop
+            assert hseg[h + 1] - hseg[h] > 2
+            acc, previous = 0.0, -1
+            for code in sec["heavy_contrib"][hseg[h] : hseg[h + 1]]:
+                value, previous = lookup(code, previous)
+                acc += value
+            store(position, acc)
+        chunks = sec["row_chunk"].reshape(-1, 8)
+        visited = np.zeros(len(chunks), dtype=bool)
         for j, row in enumerate(sec["row_id"]):  # load entry + diagonal share the row's element list
             rhs = diag = 0.0
-            for code in sec["lcontrib"][lseg[j] : lseg[j + 1]]:
-                k, el = divmod(int(code), stride)
-                assert k < 3
-                rhs += sloc[6 + k, el]
-                diag += sloc[k, el]
+            ch = j
+            while True:
+                assert not visited[ch]
+                visited[ch] = True
+                for code in chunks[ch, :7]:
+                    k, el = divmod(int(code), stride)
+                    assert k < 3 and (el < n_elem or code == zero_code)
+                    rhs += table[6 + k, el]
+                    diag += table[k, el]
+                ch = int(chunks[ch, 7])
+                if ch == 0:
+                    break
+                assert ch >= sec["n_rows"]
             load[row] = rhs
             if sec["row_diag"][j] != 0xFFFFFFFF:
                 store(sec["row_diag"][j], diag)
+        assert visited.all()
     return csr_val, load

@@ -9,11 +9,29 @@ from pytorch_fem_solver_b200 import csr, meshgen
 from tests.plan_emulator import emulate_tiled
 
 
+def fan_mesh(n):
+    """n triangles around one centre vertex: its row needs several 7-element chunks in the tile plan."""
+    angle = 2 * np.pi * np.arange(n) / n
+    vertices = np.concatenate([[[0.5, 0.5]], 0.5 + 0.4 * np.stack([np.cos(angle), np.sin(angle)], 1)])
+    triangles = np.stack([np.zeros(n, dtype=np.int64), 1 + np.arange(n), 1 + (np.arange(n) + 1) % n], 1).astype(np.int32)
+    return {"vertices": vertices, "triangles": triangles}
+
+
+def nonmanifold_mesh():
+    """Three triangles on one edge (entries with 3 contributions), a triangle with a repeated
+    vertex (a diagonal that also receives off-diagonal slots) and an isolated vertex."""
+    vertices = np.array([[0.0, 0.0], [1.0, 0.0], [0.5, 0.8], [0.5, -0.7], [0.4, 0.3], [0.9, 0.9], [0.1, 0.9], [2.0, 2.0]])
+    triangles = np.array([[0, 1, 2], [1, 0, 3], [0, 1, 4], [2, 5, 6], [2, 2, 5], [4, 1, 2]], dtype=np.int32)
+    return {"vertices": vertices, "triangles": triangles}
+
+
 def meshes():
     yield "structured4x4", meshgen.structured_rectangle(4, 4, topology=False)
     yield "structured37x21_jitter", meshgen.structured_rectangle(37, 21, jitter=0.25, seed=2, topology=False)
     yield "delaunay200", meshgen.delaunay_unit_square(200, seed=4)
     yield "permuted", meshgen.permute_mesh(meshgen.structured_rectangle(24, 24, jitter=0.2, topology=False))
+    yield "fan23", fan_mesh(23)
+    yield "nonmanifold", nonmanifold_mesh()
 
 
 @pytest.mark.parametrize("name,mesh", list(meshes()))
@@ -54,6 +72,11 @@ def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
     local = fo.quad_reduce(fo.form_stiffness_mass(geo), geo["dx"])
     f_q = fo.source_sinsin(geo["integration_points"])
     lvec = fo.quad_reduce(fo.form_load(geo, f_q), geo["dx"]).reshape(-1, 3)
+    if not np.isfinite(local).all():  # degenerate element: any symmetric local matrices exercise the plan
+        rng = np.random.default_rng(0)
+        local = rng.standard_normal(local.shape)
+        local = local + np.swapaxes(local, -1, -2)
+        lvec = rng.standard_normal(lvec.shape)
     vals, load = emulate_tiled(plan, coords, local, lvec, conn, pat.nnz, n_dof)
     crow, col, ref_vals = fo.scatter_bilinear_csr(local, conn, n_dof)
     ref_load = fo.scatter_linear(lvec, conn, n_dof).reshape(-1)
