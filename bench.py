@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--nx", type=int, default=NX)
     p.add_argument("--ny", type=int, default=NY)
     p.add_argument("--path", default="tiled", choices=["tiled", "two_pass"])
-    p.add_argument("--rows-per-tile", type=int, default=160)
+    p.add_argument("--rows-per-tile", type=int, default=192)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()

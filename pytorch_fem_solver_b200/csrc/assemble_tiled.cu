@@ -83,18 +83,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// Bounded spin: a protocol bug traps instead of hanging the GPU.
+// Bounded wait: a protocol bug traps instead of hanging the GPU.  The suspend-time hint lets the
+// hardware park the warp until the phase completes (or ~20 us pass) instead of polling, so waiting
+// warps do not compete for issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
-    if (spin > (1u << 24)) __trap();
+    if (spin > (1u << 20)) __trap();
   }
 }
 template <int BYTES>
@@ -120,6 +122,18 @@ template <> struct NQ<4> { static constexpr int value = 6; };
 
 __device__ __forceinline__ void sincos_full(double x, double& s, double& c) { sincos(x, &s, &c); }
 __device__ __forceinline__ void sincos_full(float x, float& s, float& c) { sincosf(x, &s, &c); }
+
+// Magnitude keys: order-preserving integer images of |v| (the high word for doubles), so that the
+// largest of several magnitudes and a threshold test cost integer min/max instead of fp64 compares.
+__device__ __forceinline__ int mag_key(double v) { return __double2hiint(v) & 0x7fffffff; }
+__device__ __forceinline__ int mag_key(float v) { return __float_as_int(v) & 0x7fffffff; }
+template <typename T> struct MagKey;
+template <> struct MagKey<double> {  // high words of 0.008, 0.02, 0.03, 0.1 (low word dropped: slightly stricter)
+  static constexpr int k008 = 0x3F80624D, k02 = 0x3F947AE1, k03 = 0x3F9EB851, k1 = 0x3FB99999;
+};
+template <> struct MagKey<float> {
+  static constexpr int k008 = 0x3C03126E, k02 = 0x3CA3D70A, k03 = 0x3CF5C28F, k1 = 0x3DCCCCCC;
+};
 
 // sin(t), cos(t) for |t| <= 0.02 (truncation < 1e-18 relative)
 template <typename T>
@@ -152,9 +166,11 @@ __device__ __forceinline__ void sincos_medium(T t, T& s, T& c) {
 template <typename T>
 __device__ __forceinline__ void sincos_about(T w, T x, T xb, T sb, T cb, T& s, T& c) {
   const T th = w * (x - xb);
-  if (fabs(th) <= T(0.1)) {
+  const int key = mag_key(th);
+  if (key < MagKey<T>::k1) {
     T st, ct;
-    sincos_medium(th, st, ct);
+    if (key < MagKey<T>::k02) sincos_small(th, st, ct);  // the usual case: a tile spans a few elements
+    else sincos_medium(th, st, ct);
     s = fma(sb, ct, cb * st);
     c = fma(cb, ct, -(sb * st));
   } else {
@@ -217,18 +233,6 @@ __device__ __forceinline__ LbView view_lb(const int32_t* b, const EView& e) {
   return v;
 }
 
-// Magnitude keys: order-preserving integer images of |v| (the high word for doubles), so that the
-// largest of several magnitudes and a threshold test cost integer min/max instead of fp64 compares.
-__device__ __forceinline__ int mag_key(double v) { return __double2hiint(v) & 0x7fffffff; }
-__device__ __forceinline__ int mag_key(float v) { return __float_as_int(v) & 0x7fffffff; }
-template <typename T> struct MagKey;
-template <> struct MagKey<double> {  // high words of 0.008 and 0.03 (low word dropped: slightly stricter)
-  static constexpr int k008 = 0x3F80624D, k03 = 0x3F9EB851;
-};
-template <> struct MagKey<float> {
-  static constexpr int k008 = 0x3C03126E, k03 = 0x3CF5C28F;
-};
-
 // sin(a + t) as a polynomial in t with coefficients k[] = {sin a, cos a, -sin a/2, -cos a/6, ...}
 template <typename T, int DEG>
 __device__ __forceinline__ void shifted_sine_coefficients(T s, T c, T (&k)[DEG + 1]) {
@@ -263,7 +267,7 @@ __device__ __forceinline__ void sinsin_moments(T sx0, T cx0, T sy0, T cy0, T uax
 }
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
-__global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_CTAS_128 : (CONSUMERS == 256 ? TFEM_MIN_CTAS : 2))) assemble_tiled_kernel(
+__global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_CTAS_128 : (CONSUMERS == 192 ? 4 : (CONSUMERS == 256 ? TFEM_MIN_CTAS : 2)))) assemble_tiled_kernel(
     const int n_tiles, const int32_t* __restrict__ tile_list, const int32_t* __restrict__ e_off, const int32_t* __restrict__ e_blob,
     const int32_t* __restrict__ la_off, const int32_t* __restrict__ la_blob, const int32_t* __restrict__ lb_off,
     const int32_t* __restrict__ lb_blob, const int max_vert, const int elem_stride, const int e_words,
@@ -643,6 +647,7 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
     default: return dispatch_tiled<T, C, 4>(hp, coords, quad, alpha, beta, src, csr_val, load, s);        \
   }
   if (consumers == 128) { TFEM_DISPATCH_ORDER(128) }
+  if (consumers == 192) { TFEM_DISPATCH_ORDER(192) }
   if (consumers == 256) { TFEM_DISPATCH_ORDER(256) }
   if (consumers == 384) { TFEM_DISPATCH_ORDER(384) }
   if (consumers == 512) { TFEM_DISPATCH_ORDER(512) }

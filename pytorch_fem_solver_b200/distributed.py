@@ -244,7 +244,7 @@ class StripAssembly:
     `step()` assembles the tiles holding interface rows first, then the interior tiles on the main
     stream while the interface exchange (pack -> NCCL send/recv -> add) runs on a side stream."""
 
-    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=160, group=None, exchange_ops=None):
+    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=192, group=None, exchange_ops=None):
         import numpy as np
 
         from . import ElementTri, MeshTri, forms

@@ -216,7 +216,7 @@ def build_tile_plan(
     dof_conn: torch.Tensor,
     pattern: CsrPattern,
     row_points: torch.Tensor | None = None,
-    rows_per_tile: int = 160,
+    rows_per_tile: int = 192,
     ordering: str = "block",
 ) -> TilePlan:
     """Partition CSR rows into tiles and precompute everything the fused kernel gathers.
