@@ -185,7 +185,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -197,8 +197,9 @@ def workload_config(args):
         "path": args.path,
         "l2": "flushed between timed steps (256 MiB write)",
         "symbolic": "CSR pattern + tile plan built once, outside the timed region",
-        "multi_gpu": "weak scaling: one strip of the same size per GPU, interface rows packed, all-gathered over NCCL and "
-        "added by their owners on a side stream while the interior tiles assemble",
+        "multi_gpu": "weak scaling: one strip of the same size per GPU; interface rows are packed straight into the owner's "
+        "receive buffer over NVLink peer memory (signal-pad handshake; TFEM_EXCHANGE=nccl selects one all_gather instead) "
+        "and added by their owners on a side stream while the interior tiles assemble",
     }
 
 
@@ -258,6 +259,7 @@ def run_ours(args):
         # interface tiles first, then interior tiles while the NCCL exchange runs on a side stream
         step = assembler.step
         kernels_per_step = 2 + assembler.fused_exchange.n_kernels
+        exchange_kind = type(assembler.fused_exchange).__name__
     elif assembler is not None:
 
         def step():
@@ -386,6 +388,8 @@ def run_ours(args):
                 "bytes_per_element": algorithmic / n_el,
             },
         }
+        if assembler is not None and args.path == "tiled":
+            line["config"]["exchange"] = exchange_kind
         if plan is not None:
             line["config"]["tile_plan"] = {"tiles": plan.n_tiles, "rows_per_tile": args.rows_per_tile, "halo_factor": round(plan.halo_factor, 4),
                                            "index_bytes": plan.index_bytes, "max_vert": plan.max_vert, "max_elem": plan.max_elem, "max_out": plan.max_out}
@@ -403,14 +407,29 @@ def run_ours(args):
             cpu_value, sample, timings = cpu_reference_run(args.nx, args.ny, repeats=2)
             line["cpu_baseline"] = {"value": cpu_value, "unit": "elements/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": sample, "host_cpus": os.cpu_count(), "stage_seconds": timings}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is exactly one
+    # JSON line on stdout, so everything else is sent to stderr.
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -121,7 +121,13 @@ typedef struct tfem_tile_plan {
   int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = choose from max_elem */
   int32_t elem_stride;      /* row length of the local-matrix table, > max_elem (last column = zeros), multiple of 32 */
   int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
-                               (interface pack / NCCL send-recv / add) can run beside it; 0 = use every slot */
+                               (interface pack / signal / add) can run beside it; 0 = use every slot */
+  int32_t n_progress_tiles; /* the first n_progress_tiles tiles of the call (in tile_list order) report on
+                               `progress` when they are finished: every consumer warp adds 1 after its stores
+                               (release), so the counter grows by n_progress_tiles * consumer_threads / 32 per
+                               call; 0 = nobody reports */
+  uint32_t* progress;       /* device counter, never reset by the library (callers wait for a growing target
+                               with tfem_iface_pack_after); NULL = nobody reports */
 } tfem_tile_plan;
 
 int tfem_abi_version(void);
@@ -235,6 +241,12 @@ int tfem_sm_count(void);
    * contiguous send buffer, and add a received buffer into the owner's entries                  \
    * (idx entries are unique, so no atomics). */                                                 \
   int tfem_iface_pack_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf, void* stream);    \
+  /* The same gather, started early: every block first waits (bounded spin, then trap) until the   \
+   * device counter `progress` has reached `target` (wrap-safe), i.e. until the tiles holding the  \
+   * interface rows of a tfem_tri_p1_assemble_csr call running beside it are complete.  `buf`      \
+   * may be peer memory (NVLink). */                                                             \
+  int tfem_iface_pack_after_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf,             \
+                                  const uint32_t* progress, uint32_t target, void* stream);        \
   int tfem_iface_unpack_add_##SUF(int64_t n, const int32_t* idx, const T* buf, T* dst,             \
                                   void* stream);
 

@@ -11,7 +11,7 @@ import ctypes
 import os
 import re
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 import torch
 
@@ -59,6 +59,8 @@ class TilePlan(Structure):
         ("consumer_threads", c_int32),
         ("elem_stride", c_int32),
         ("reserve_ctas", c_int32),
+        ("n_progress_tiles", c_int32),
+        ("progress", c_void_p),
     ]
 
 
@@ -80,6 +82,7 @@ _TYPED = {
     "tfem_interp_edges_bwd": [I64, I64, I64, P, P, P, c_int, P, c_int, P, P, P, P],
     "tfem_edge_jump": [I64, c_int, c_int, P, P, P, P, P, P],
     "tfem_iface_pack": [I64, P, P, P, P],
+    "tfem_iface_pack_after": [I64, P, P, P, P, c_uint32],
     "tfem_iface_unpack_add": [I64, P, P, P, P],
 }
 _UNTYPED = {

@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_C
     const int n_tiles, const int32_t* __restrict__ tile_list, const int32_t* __restrict__ e_off, const int32_t* __restrict__ e_blob,
     const int32_t* __restrict__ la_off, const int32_t* __restrict__ la_blob, const int32_t* __restrict__ lb_off,
     const int32_t* __restrict__ lb_blob, const int max_vert, const int elem_stride, const int e_words,
-    const int la_words, const int lb_words, const T* __restrict__ coords,
+    const int la_words, const int lb_words, uint32_t* __restrict__ progress, const int n_progress,
+    const T* __restrict__ coords,
     const QuadT<T> quad, const T alpha, const T beta, const SourceT<T> src, T* __restrict__ csr_val,
     T* __restrict__ load) {
   constexpr int NQV = NQ<ORDER>::value;
@@ -556,6 +557,13 @@ __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_C
     // tile's phase A only writes trig (not read in phase C) and ends in a block barrier before sloc is
     // written again, so each warp just reports to the producer; otherwise the block barrier stays.
     if constexpr (!SINSIN) consumer_sync<CONSUMERS>();
+    if (progress != nullptr && (int)blockIdx.x + it * (int)gridDim.x < n_progress) {
+      // the first tiles of the call hold the multi-GPU interface rows: tell the exchange kernels
+      // waiting on the counter (tfem_iface_pack_after) that this warp's stores are out
+      __threadfence();
+      __syncwarp();
+      if ((tid & 31) == 0) atomicAdd(progress, 1u);
+    }
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(done_bar + buf);
     TFEM_T(5);
@@ -596,7 +604,8 @@ int launch_tiled(const tfem_tile_plan* hp, const T* coords, const QuadT<T>& quad
   if (hp->reserve_ctas > 0 && resident > hp->reserve_ctas) resident -= hp->reserve_ctas;  // room for concurrent kernels
   const unsigned grid = (unsigned)(hp->n_tiles < resident ? hp->n_tiles : resident);
   kern<<<grid, CONSUMERS + 32, smem, s>>>((int)hp->n_tiles, hp->tile_list, hp->e_off, hp->e_blob, hp->la_off, hp->la_blob, hp->lb_off,
-                                         hp->lb_blob, hp->max_vert, elem_stride, e_words, la_words, lb_words, coords, quad, alpha, beta, src, csr_val, load);
+                                         hp->lb_blob, hp->max_vert, elem_stride, e_words, la_words, lb_words,
+                                         hp->n_progress_tiles > 0 ? hp->progress : nullptr, hp->n_progress_tiles, coords, quad, alpha, beta, src, csr_val, load);
   return check_launch();
 }
 

@@ -66,6 +66,38 @@ int segment_reduce(int64_t n_out, const int32_t* seg, const int32_t* perm, const
   return check_launch();
 }
 
+// pack_kernel behind a device-side dependency: wait until `progress` (bumped with release semantics by
+// the assembly kernel's warps) has reached `target`; the comparison is wrap-safe.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_after_kernel(int n, const int32_t* __restrict__ idx, const T* src,
+                                                         T* __restrict__ buf, const uint32_t* progress, uint32_t target) {
+  if (threadIdx.x == 0) {
+    uint32_t seen;
+    for (uint32_t spin = 0;; ++spin) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(progress) : "memory");
+      if ((int32_t)(seen - target) >= 0) break;
+      if (spin > (1u << 26)) __trap();  // a few seconds: the producer never ran
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  // src is being written by another kernel during this launch: plain loads, no __ldg
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = src[__ldg(idx + i)];
+}
+
+template <typename T>
+int iface_pack_after(int64_t n, const int32_t* idx, const T* src, T* buf, const uint32_t* progress, uint32_t target,
+                     void* stream) {
+  if (n < 0) return TFEM_ERR_BAD_ARG;
+  if (n == 0) return TFEM_OK;
+  if (!idx || !src || !buf || !progress) return TFEM_ERR_BAD_ARG;
+  if (n > kMaxIndex) return TFEM_ERR_TOO_LARGE;
+  // at most 16 small blocks: they spin beside a persistent grid and must fit in the slots it leaves free
+  const unsigned blocks = blocks_for(n, 256) < 16u ? blocks_for(n, 256) : 16u;
+  pack_after_kernel<T><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, idx, src, buf, progress, target);
+  return check_launch();
+}
+
 template <typename T>
 int iface_pack(int64_t n, const int32_t* idx, const T* src, T* buf, void* stream) {
   if (n < 0) return TFEM_ERR_BAD_ARG;
@@ -100,6 +132,10 @@ int iface_unpack_add(int64_t n, const int32_t* idx, const T* buf, T* dst, void* 
   extern "C" int tfem_iface_pack_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf,         \
                                        void* stream) {                                              \
     return tfem::iface_pack<T>(n, idx, src, buf, stream);                                           \
+  }                                                                                                 \
+  extern "C" int tfem_iface_pack_after_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf,   \
+                                             const uint32_t* progress, uint32_t target, void* stream) { \
+    return tfem::iface_pack_after<T>(n, idx, src, buf, progress, target, stream);                   \
   }                                                                                                 \
   extern "C" int tfem_iface_unpack_add_##SUF(int64_t n, const int32_t* idx, const T* buf, T* dst,   \
                                              void* stream) {                                        \

@@ -228,14 +228,107 @@ class FusedExchange:
         self.flat_gather = dist.get_backend(plan.group) == "nccl"
 
     def __call__(self, buffer: torch.Tensor):
+        self.pack(buffer)
+        self.gather_add(buffer)
+
+    def pack(self, buffer: torch.Tensor):
         if self.send_idx.numel():
             self.ops.pack_into(self.send_buf[: self.send_idx.numel()], buffer, self.send_idx)
+
+    def gather_add(self, buffer: torch.Tensor):
         if self.flat_gather:
             dist.all_gather_into_tensor(self.gathered, self.send_buf, group=self.plan.group)
         else:  # gloo (CPU tests) has no flat all-gather
             dist.all_gather(list(self.gathered.unbind(0)), self.send_buf, group=self.plan.group)
         for peer, idx, off, length in self.recv:  # ascending peer order -> bitwise reproducible sums
             self.ops.unpack_add(buffer, idx, self.gathered[peer, off : off + length])
+
+
+class PeerExchange:
+    """Interface exchange over NVLink peer memory (torch symmetric memory), no collective kernel.
+
+    Every rank owns a receive buffer that its peers have mapped.  Per assembly the sender's pack
+    kernel (`tfem_iface_pack`) gathers the interface entries of `[csr values | load]` and stores them
+    STRAIGHT INTO THE OWNER'S BUFFER over NVLink, then raises a signal in the owner's signal pad;
+    the owner waits for the signal on its side stream, adds the slice (`tfem_iface_unpack_add`,
+    ascending peer order, so sums are bitwise reproducible) and hands the buffer back with a second
+    signal.  Receive buffers alternate between two halves by step parity, so a sender never
+    overwrites data its owner has not added yet.  All kernels are a single small CTA-group each
+    and fit in the CTA slots the persistent interior launch leaves free (`reserve_ctas`), which a
+    NCCL collective kernel does not: behind a persistent grid it would only start when the grid ends."""
+
+    DATA, FREE = 0, 2  # signal channels: DATA + parity, FREE + parity
+
+    def __init__(self, plan: InterfacePlan, nnz: int, dtype: torch.dtype, device, exchange_ops: Optional[ExchangeOps] = None,
+                 timeout_ms: int = 20000):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.plan = plan
+        self.ops = exchange_ops or cuda_exchange_ops()
+        self.timeout_ms = timeout_ms
+        world, rank = plan.world, plan.rank
+        group = plan.group if plan.group is not None else dist.group.WORLD
+        combine = lambda pair: torch.cat([pair[0], pair[1] + nnz]).to(torch.int32).contiguous()  # noqa: E731
+        sends = [(o, combine(plan.send_idx[o])) for o in sorted(plan.send_idx)]
+        recvs = [(p, combine(plan.recv_idx[p])) for p in sorted(plan.recv_idx)]
+        # where each sender's slice starts inside MY buffer; every rank learns its offsets at its owners
+        offsets = torch.zeros(world, dtype=torch.int64, device=device)
+        lengths = torch.zeros(world, dtype=torch.int64, device=device)
+        used = 0
+        for p, idx in recvs:
+            offsets[p], lengths[p] = used, idx.numel()
+            used += idx.numel()
+        table = [torch.zeros(2 * world, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(table, torch.cat([offsets, lengths]), group=group)
+        cap = torch.tensor([used], dtype=torch.int64, device=device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
+        self.capacity = max(int(cap.item()), 1)
+        self.buf = symm_mem.empty(2 * self.capacity, dtype=dtype, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.sends = []  # (owner, local gather positions, [view of the owner's buffer half 0, half 1])
+        for o, idx in sends:
+            off, length = int(table[o][rank]), int(table[o][world + rank])
+            assert length == idx.numel(), "interface key lists disagree between sender and owner"
+            remote = self.handle.get_buffer(o, (2 * self.capacity,), dtype)
+            halves = [remote[h * self.capacity + off : h * self.capacity + off + length] for h in (0, 1)]
+            self.sends.append((o, idx, halves))
+        self.recvs = []  # (peer, local positions, [my buffer half 0, half 1])
+        for p, idx in recvs:
+            off = int(offsets[p])
+            halves = [self.buf[h * self.capacity + off : h * self.capacity + off + idx.numel()] for h in (0, 1)]
+            self.recvs.append((p, idx, halves))
+        self.steps = 0
+        self.bytes_per_exchange = sum(idx.numel() for _, idx, _ in self.sends) * self.buf.element_size()
+        self.n_kernels = len(self.sends) + len(self.recvs)
+        dist.barrier(group=group)  # every rank has mapped its peers before the first store
+
+    def __call__(self, buffer: torch.Tensor):
+        self.pack(buffer)
+        self.gather_add(buffer)
+
+    def pack(self, buffer: torch.Tensor, progress: Optional[torch.Tensor] = None, target: int = 0):
+        """With `progress`, the pack kernels wait ON THE DEVICE for the assembly launch running beside
+        them to finish its interface tiles (counter >= target) instead of for a stream event."""
+        half = self.steps & 1
+        for owner, idx, halves in self.sends:
+            if self.steps >= 2:  # the owner has added what this half held two steps ago
+                self.handle.wait_signal(owner, self.FREE + half, self.timeout_ms)
+            if progress is None:
+                self.ops.pack_into(halves[half], buffer, idx)
+            else:
+                from . import ops
+
+                ops.pack_after_raw(halves[half], buffer, idx, progress, target)
+            self.handle.put_signal(owner, self.DATA + half, self.timeout_ms)
+
+    def gather_add(self, buffer: torch.Tensor):
+        half = self.steps & 1
+        for peer, idx, halves in self.recvs:  # ascending peer order -> bitwise reproducible sums
+            self.handle.wait_signal(peer, self.DATA + half, self.timeout_ms)
+            self.ops.unpack_add(buffer, idx, halves[half])
+            self.handle.put_signal(peer, self.FREE + half, self.timeout_ms)
+        self.steps += 1
 
 
 class StripAssembly:
@@ -271,18 +364,42 @@ class StripAssembly:
         self.quad_order = quad_order
         self.buffer = torch.empty(pat.nnz + pat.n_dof, dtype=self.basis.dtype, device=device)
         self.values, self.load = self.buffer[: pat.nnz], self.buffer[pat.nnz :]
-        self.fused_exchange = FusedExchange(self.plan, pat.nnz, self.basis.dtype, device, exchange_ops)
+        self.fused_exchange = self._make_exchange(pat.nnz, device, exchange_ops)
         full = self.basis.tile_plan(rows_per_tile)
         interface_local = torch.searchsorted(self.plan.local_to_global, self.plan.interface_global)
         is_interface_tile = torch.zeros(full.n_tiles, dtype=torch.bool, device=device)
         is_interface_tile[full.tile_of_row[interface_local]] = True
         self.interface_tiles = full.subset(torch.nonzero(is_interface_tile, as_tuple=True)[0])
         # the interior launch leaves some CTA slots free so the exchange kernels can run beside it
-        reserve = int(os.environ.get("TFEM_RESERVE_CTAS", "24"))
+        reserve = int(os.environ.get("TFEM_RESERVE_CTAS", "8"))
         self.interior_tiles = full.subset(torch.nonzero(~is_interface_tile, as_tuple=True)[0], reserve_ctas=reserve)
         self.full_plan = full
+        # one launch, interface tiles first, counted on a device counter the pack kernels wait for
+        self.progress = torch.zeros(1, dtype=torch.int32, device=device)
+        ids = torch.cat([self.interface_tiles.tile_list, self.interior_tiles.tile_list])
+        self.n_interface_tiles = int(self.interface_tiles.tile_list.numel())
+        self.ordered_tiles = full.subset(ids, reserve_ctas=reserve, n_progress_tiles=self.n_interface_tiles, progress=self.progress)
+        self.progress_target = 0
         self.source = forms.SinSinSource()
         self.side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+        self.single_launch = isinstance(self.fused_exchange, PeerExchange) and os.environ.get("TFEM_SINGLE_LAUNCH", "1") == "1"
+        self._debug_no_exchange = os.environ.get("TFEM_DEBUG_NO_EXCHANGE", "0") == "1"
+        self._previous_step = torch.cuda.Event() if self.side_stream is not None else None
+        if self._previous_step is not None:
+            self._previous_step.record(torch.cuda.current_stream())
+
+    def _make_exchange(self, nnz, device, exchange_ops):
+        """Peer-memory stores + signals on NVLink when the ranks are CUDA peers (TFEM_EXCHANGE=peer, the
+        default with NCCL), else one all-gather (TFEM_EXCHANGE=nccl; gloo in the CPU tests)."""
+        kind = os.environ.get("TFEM_EXCHANGE", "peer" if dist.get_backend(self.plan.group) == "nccl" else "nccl")
+        if kind == "peer":
+            try:
+                return PeerExchange(self.plan, nnz, self.basis.dtype, device, exchange_ops)
+            except Exception as error:  # no P2P mapping between these devices: say so, use the collective
+                import sys
+
+                print(f"[tfem] peer-memory exchange unavailable ({error!r}); using all_gather", file=sys.stderr)
+        return FusedExchange(self.plan, nnz, self.basis.dtype, device, exchange_ops)
 
     def _launch(self, plan, alpha, beta):
         from . import ops
@@ -293,11 +410,29 @@ class StripAssembly:
     def step(self, alpha: float = 1.0, beta: float = 1.0):
         """One distributed assembly into `self.values` / `self.load` (owned rows complete)."""
         main = torch.cuda.current_stream()
+        if self._debug_no_exchange:  # profiling aid: the assembly launch alone (results incomplete on interface rows)
+            self._launch(self.ordered_tiles, alpha, beta)
+            return
+        if self.single_launch:
+            # ONE persistent launch walks the interface tiles first and counts them on a device
+            # counter; the pack kernels on the side stream wait for that counter, store over NVLink
+            # into the owners' buffers and signal, while the same launch goes on with the interior
+            self.progress_target += self.n_interface_tiles * self.ordered_tiles.consumer_warps
+            self._launch(self.ordered_tiles, alpha, beta)
+            with torch.cuda.stream(self.side_stream):
+                self.side_stream.wait_event(self._previous_step)  # the buffer's previous contents are final
+                self.fused_exchange.pack(self.buffer, self.progress, self.progress_target)
+                self.fused_exchange.gather_add(self.buffer)
+                finished = torch.cuda.Event()
+                finished.record(self.side_stream)
+            main.wait_event(finished)
+            self._previous_step.record(main)
+            return
         self._launch(self.interface_tiles, alpha, beta)
         ready = torch.cuda.Event()
         ready.record(main)
         # enqueue the long interior launch BEFORE the exchange so the GPU is busy while the host issues
-        # the (comparatively slow to enqueue) pack / all-gather / add sequence on the side stream
+        # the pack / exchange / add sequence on the side stream
         self._launch(self.interior_tiles, alpha, beta)
         with torch.cuda.stream(self.side_stream):
             self.side_stream.wait_event(ready)

@@ -218,6 +218,13 @@ def pack_into_raw(out: Tensor, src: Tensor, idx: Tensor) -> None:
     call("tfem_iface_pack", src.dtype, device, idx.shape[0], ptr(idx), ptr(src), ptr(out))
 
 
+def pack_after_raw(out: Tensor, src: Tensor, idx: Tensor, progress: Tensor, target: int) -> None:
+    """`pack_into_raw` that starts early and waits on the device until the assembly kernel running
+    beside it has bumped `progress` to `target` (see tfem_iface_pack_after)."""
+    device = check_cuda(out, src, idx, progress)
+    call("tfem_iface_pack_after", src.dtype, device, idx.shape[0], ptr(idx), ptr(src), ptr(out), ptr(progress), target & 0xFFFFFFFF)
+
+
 def unpack_add_raw(dst: Tensor, idx: Tensor, buf: Tensor) -> None:
     """dst[idx[i]] += buf[i] (unique idx): direct C-ABI call for per-step hot loops."""
     device = check_cuda(dst, idx, buf)

@@ -142,6 +142,8 @@ class TilePlan:
     tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
     tile_list: torch.Tensor = None  # optional (n,) int32 subset of tiles to run (see `subset`)
     reserve_ctas: int = 0  # CTA slots left free for kernels on other streams while this plan runs
+    n_progress_tiles: int = 0  # the first tiles of `tile_list` report on `progress` when finished
+    progress: torch.Tensor = None  # (1,) int32 device counter (see include/tfem_b200.h)
 
     def c_struct(self) -> "_lib.TilePlan":
         s = _lib.TilePlan()
@@ -154,15 +156,24 @@ class TilePlan:
         s.max_la_words, s.max_lb_words = self.max_la_words, self.max_lb_words
         s.elem_stride = self.elem_stride
         s.reserve_ctas = self.reserve_ctas
+        s.n_progress_tiles = self.n_progress_tiles if self.progress is not None else 0
+        s.progress = None if self.progress is None else self.progress.data_ptr()
         s.consumer_threads = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads))
         return s
 
-    def subset(self, tile_ids: torch.Tensor, reserve_ctas: int = 0) -> "TilePlan":
-        """The same plan restricted to some tiles (shares every array); used to assemble the tiles
-        that hold multi-GPU interface rows first and the rest while the exchange is in flight."""
+    def subset(self, tile_ids: torch.Tensor, reserve_ctas: int = 0, n_progress_tiles: int = 0, progress: torch.Tensor = None) -> "TilePlan":
+        """The same plan restricted to / reordered over some tiles (shares every array); used to
+        assemble the tiles that hold multi-GPU interface rows first, with the first
+        `n_progress_tiles` of them counted on `progress` so the exchange can start mid-launch."""
         import dataclasses
 
-        return dataclasses.replace(self, tile_list=tile_ids.to(torch.int32).contiguous(), reserve_ctas=reserve_ctas)
+        return dataclasses.replace(self, tile_list=tile_ids.to(torch.int32).contiguous(), reserve_ctas=reserve_ctas,
+                                   n_progress_tiles=n_progress_tiles, progress=progress)
+
+    @property
+    def consumer_warps(self) -> int:
+        """Warps that report per finished tile on `progress` (library default: 256 consumer threads)."""
+        return (int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)) or 256) // 32
 
     def to(self, device) -> "TilePlan":
         moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}

@@ -1,0 +1,6 @@
+run() { n=$1; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 30 --warmup 5 --no-cpu-baseline --no-e2e 2>gpurun_out/ab.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('n',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],d['config'].get('exchange'))"; }
+echo "== N=8 peer single, reserve 8"; TFEM_RESERVE_CTAS=8 run 8
+echo "== N=8 peer single, reserve 24"; TFEM_RESERVE_CTAS=24 run 8
+echo "== N=4 peer single, reserve 8"; TFEM_RESERVE_CTAS=8 run 4
