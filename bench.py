@@ -17,8 +17,8 @@ load f = 2 pi^2 sin(pi x) sin(pi y)) into CSR values + load vector.  Prints ONE 
 
 `--impl reference` times that CPU port alone (the reference is pure Python and does not exist on
 the GPU box).  Multi-GPU (`torchrun`, one rank per GPU): weak scaling, each rank
-assembles its own 4.19 M-element strip of a mesh that is N times taller, interface rows are
-summed over NCCL.
+assembles its own 4.19 M-element strip of a mesh that is N times taller; interface rows travel
+over NVLink peer memory while the interior assembles.
 """
 
 from __future__ import annotations

@@ -334,3 +334,40 @@ def test_jump_estimator_gradient_matches_torch_autograd():
     assert relmax(eta.detach().reshape(-1).cpu().numpy(), eta_r.detach().cpu().numpy()) < 1e-12
     (g_ref,) = torch.autograd.grad((eta_r * weights.reshape(-1)).sum() + 0.1 * (val_r**2).sum(), u_ref)
     assert relmax(g_ours.cpu().numpy(), g_ref.cpu().numpy()) < 1e-12
+
+
+def test_progress_counter_releases_waiting_pack():
+    """Device-side dependency of the multi-GPU step: tiles listed first report on a counter, and
+    tfem_iface_pack_after (started EARLIER, on another stream) gathers their rows once they are done."""
+    from pytorch_fem_solver_b200 import ops
+
+    mesh = meshgen.structured_rectangle(96, 64, jitter=0.2, seed=11, topology=False)
+    basis = make_basis(mesh, 3)
+    pat = basis.pattern
+    plan = basis.tile_plan(64)
+    first = 5
+    progress = torch.zeros(1, dtype=torch.int32, device=DEV)
+    order = torch.arange(plan.n_tiles, device=DEV).flip(0)  # any order: the LAST tiles are listed first here
+    ordered = plan.subset(order, reserve_ctas=8, n_progress_tiles=first, progress=progress)
+    rows = torch.nonzero(plan.tile_of_row >= plan.n_tiles - first, as_tuple=True)[0]
+    crow = pat.crow.long()
+    idx = torch.cat([torch.arange(int(crow[r]), int(crow[r + 1]), device=DEV) for r in rows.tolist()] + [pat.nnz + rows]).to(torch.int32)
+    buffer = torch.zeros(pat.nnz + pat.n_dof, dtype=torch.float64, device=DEV)
+    values, load = buffer[: pat.nnz], buffer[pat.nnz :]
+    src = forms.SinSinSource()
+    side = torch.cuda.Stream()
+    outs = []
+    for step in (1, 2):
+        buffer.zero_()
+        torch.cuda.synchronize()
+        out = torch.full((idx.numel(),), -1.0, dtype=torch.float64, device=DEV)
+        with torch.cuda.stream(side):  # enqueued first: it has to wait on the device
+            ops.pack_after_raw(out, buffer, idx, progress, step * first * ordered.consumer_warps)
+        ops.assemble_csr_tiled(ordered.c_struct(), basis._layout.coords, 3, 0.7, 1.3, src.kind, src.params, values, load)
+        torch.cuda.synchronize()
+        assert int(progress.item()) == step * first * ordered.consumer_warps
+        assert torch.equal(out, buffer[idx.long()])
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    crow_o, col_o, ref_vals, ref_load = oracle_system(mesh, 3, 0.7, 1.3)
+    assert relmax(values.cpu().numpy(), ref_vals) < 1e-12 and relmax(load.cpu().numpy(), ref_load) < 1e-12
