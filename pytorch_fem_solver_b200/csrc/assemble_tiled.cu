@@ -83,12 +83,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU.  The suspend-time hint lets the
-// hardware park the warp until the phase completes (or ~20 us pass) instead of polling, so waiting
-// warps do not compete for issue slots.
+// Bounded wait: a protocol bug traps (after ~4 s of wall time) instead of hanging the GPU.  The
+// suspend-time hint lets the hardware park the warp instead of polling.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
+  uint64_t started = 0;
+  for (uint32_t spin = 1; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -96,7 +101,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
-    if (spin > (1u << 20)) __trap();
+    if ((spin & 0x3fffu) == 0) {  // every 16384 polls: look at the wall clock
+      const uint64_t now = global_timer_ns();
+      if (started == 0) started = now;
+      else if (now - started > 4000000000ull) __trap();
+    }
   }
 }
 template <int BYTES>

@@ -361,6 +361,7 @@ def test_progress_counter_releases_waiting_pack():
         buffer.zero_()
         torch.cuda.synchronize()
         out = torch.full((idx.numel(),), -1.0, dtype=torch.float64, device=DEV)
+        side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # enqueued first: it has to wait on the device
             ops.pack_after_raw(out, buffer, idx, progress, step * first * ordered.consumer_warps)
         ops.assemble_csr_tiled(ordered.c_struct(), basis._layout.coords, 3, 0.7, 1.3, src.kind, src.params, values, load)
