@@ -315,3 +315,69 @@ def check_fractures(g, device):
             n_e = mesh["interior_edges", "normals_3d"].unsqueeze(-2)
             close(edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e), g[p + "eta"], rtol=1e-10, what="frac eta")
         return aligned
+
+
+def check_seven_fractures(device, nx=8, ny=4, order=3):
+    """BASELINE config 5 (scaled): backbone + six crossing planes.  The reference cannot represent this
+    network (fracture_basis.py:84-92 reshapes the trace edges to (F,-1)), so parity is against the
+    oracle's restatement of the same algorithm plus properties of the assembled operators."""
+    from oracle import fem_oracle as fo
+    from pytorch_fem_solver_b200 import meshgen
+
+    meshes, data = meshgen.seven_fracture_network(nx, ny)
+    v2 = np.stack([m["vertices"] for m in meshes])
+    conn = np.stack([m["triangles"] for m in meshes])
+    n_v = (nx + 1) * (ny + 1)
+    n_g = 7 * n_v - 6 * (ny + 1)  # every crossing plane shares one column of ny+1 vertices with the backbone
+    with default_device(device):
+        mesh = tfem.FracturesTri(meshes, torch.tensor(data))
+        basis = tfem.FractureBasis(mesh, tfem.ElementTri(1, order))
+        gt = basis.global_triangulation
+        assert gt["vertices_3D"].shape[-2] == n_g
+        # oracle on the same inputs
+        fmap = fo.fracture_map(v2, data)
+        v3 = fo.fracture_vertices_3d(v2, fmap)
+        close(mesh["vertices", "coordinates_3d"], v3, rtol=1e-15, what="coordinates_3d")
+        o_gt = fo.global_triangulation(v3, v2, conn, np.stack([m["edges"] for m in meshes]),
+                                       np.stack([m["vertex_markers"] for m in meshes]), np.stack([m["edge_markers"] for m in meshes]))
+        for key in ("triangles", "global2local_idx", "local2global_idx", "vertex_markers"):
+            equal(gt[key], o_gt[key], what="7 fractures " + key)
+        tris = o_gt["triangles"]
+        geo = fo.tri_geometry(v2, conn, order, fracture=fmap)
+        for form, fn in ((forms.Stiffness(), fo.form_stiffness), (forms.StiffnessMass(), fo.form_stiffness_mass)):
+            local = fo.quad_reduce(fn(geo), geo["dx"]).reshape(-1, 3, 3)
+            crow, col, vals = fo.scatter_bilinear_csr(local, tris, n_g)
+            ours = basis.integrate_bilinear_form(form)
+            if ours.layout == torch.sparse_csr:
+                equal(ours.crow_indices(), crow, what="7 fractures crow")
+                equal(ours.col_indices(), col, what="7 fractures col")
+                close(ours.values(), vals, what="7 fractures values")
+                dense_rows = None
+            else:
+                close(ours, fo.csr_to_dense(crow, col, vals, n_g), what="7 fractures matrix")
+        # stiffness annihilates constants; a trace vertex collects elements of two planes
+        k_csr = fo.scatter_bilinear_csr(fo.quad_reduce(fo.form_stiffness(geo), geo["dx"]).reshape(-1, 3, 3), tris, n_g)
+        row_sums = np.add.reduceat(k_csr[2], k_csr[0][:-1])
+        assert np.abs(row_sums).max() < 1e-12 * np.abs(k_csr[2]).max()
+        f_q = rhs3_np(geo["integration_points"])
+        b = fo.scatter_linear(fo.quad_reduce(fo.form_load(geo, f_q), geo["dx"]), tris, n_g)
+        close(basis.integrate_linear_form(forms.Load(rhs3)), b, what="7 fractures load")
+        # tangential gradient of a globally linear field is constant per plane: no jumps inside a plane
+        edges_basis = tfem.InteriorEdgesFractureBasis(mesh, tfem.ElementLine(1, 2))
+        basis2 = tfem.FractureBasis(mesh, tfem.ElementTri(1, 2))
+        nodes = mesh["vertices", "coordinates_3d"]
+        u_local = (0.3 * nodes[..., 0] - 1.1 * nodes[..., 1] + 0.7 * nodes[..., 2] + 0.2).reshape(-1, 1)
+        val, grad = basis2.interpolate(edges_basis, u_local)
+        h_e = mesh["interior_edges", "length"].unsqueeze(-2)
+        n_e = mesh["interior_edges", "normals_3d"].unsqueeze(-2)
+        eta = edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e)
+        assert float(eta.abs().max()) < 1e-20, float(eta.abs().max())
+        # (values at the edge points are not compared: like the reference, FractureBasis.interpolate
+        # to edges indexes the nodal vector with fracture-LOCAL vertex ids, fracture_basis.py:229-231)
+        assert val.shape[:3] == grad.shape[:3] == (7, mesh["interior_edges", "cells"].shape[-2], 2)
+    return n_g
+
+
+def rhs3_np(points):
+    x, y, z = np.split(points, 3, axis=-1)
+    return 6.0 * (y - y**2) * np.abs(x) - 2.0 * (np.abs(z) ** 3 - np.abs(x)) + 1.0

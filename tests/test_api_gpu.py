@@ -48,3 +48,9 @@ def test_cpu_tensors_are_refused():
     conn = torch.zeros((1, 3), dtype=torch.int32)
     with pytest.raises(_lib.TfemError):
         ops.tri_geometry(coords, conn, 1, 3, 2)
+
+
+@pytest.mark.parametrize("nx,ny", [(8, 4), (64, 32)])
+def test_seven_fracture_network(nx, ny):
+    """BASELINE config 5, scaled down (CSR output above 8192 DOFs): kernels vs the oracle + properties."""
+    assert api_checks.check_seven_fractures("cuda", nx=nx, ny=ny) == 7 * (nx + 1) * (ny + 1) - 6 * (ny + 1)

@@ -32,3 +32,9 @@ def test_patches(golden, monkeypatch):
 def test_fractures(golden, monkeypatch, name):
     cpu_shim.install(monkeypatch)
     api_checks.check_fractures(golden(name), "cpu")
+
+
+def test_seven_fracture_network(monkeypatch):
+    """BASELINE config 5, scaled down: 7 planes, 6 trace lines (the reference cannot build this one)."""
+    cpu_shim.install(monkeypatch)
+    assert api_checks.check_seven_fractures("cpu", nx=8, ny=4) == 7 * 45 - 6 * 5
