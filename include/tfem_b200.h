@@ -248,7 +248,13 @@ int tfem_sm_count(void);
   int tfem_iface_pack_after_##SUF(int64_t n, const int32_t* idx, const T* src, T* buf,             \
                                   const uint32_t* progress, uint32_t target, void* stream);        \
   int tfem_iface_unpack_add_##SUF(int64_t n, const int32_t* idx, const T* buf, T* dst,             \
-                                  void* stream);
+                                  void* stream);                                                   \
+  /* SURVEY.md 8(f).1 -- y = A x on the assembled CSR system, the operator of the iterative       \
+   * solve that replaces the dense torch.linalg.solve of basis/abstract_basis.py:177-195 when   \
+   * the matrix cannot be densified.  keep [n_rows] (0/1 bytes) or NULL: rows with keep == 0     \
+   * (Dirichlet rows of AbstractBasis.reduce, abstract_basis.py:114-117) give y = 0. */          \
+  int tfem_csr_spmv_##SUF(int64_t n_rows, const int32_t* crow, const int32_t* col, const T* val,   \
+                          const T* x, const uint8_t* keep, T* y, void* stream);
 
 TFEM_DECLARE(double, f64)
 TFEM_DECLARE(float, f32)

@@ -5,7 +5,7 @@ geometry, quadrature, weak residuals, jump terms and the local-to-global scatter
 hand-written sm_100a CUDA kernels behind the C ABI of `include/tfem_b200.h`.
 """
 
-from . import csr, forms, meshgen, ops
+from . import csr, forms, meshgen, ops, sparse
 from .basis import Basis, FractureBasis, InteriorEdgesBasis, InteriorEdgesFractureBasis, PatchesBasis
 from .element import ElementLine, ElementTri
 from .mesh import FracturesTri, MeshesTri, MeshTri, Patches
@@ -29,4 +29,5 @@ __all__ = [
     "csr",
     "meshgen",
     "ops",
+    "sparse",
 ]

@@ -326,14 +326,39 @@ class AbstractBasis(abc.ABC):
         """Zero vector of shape (nb_dofs, 1) (reference :173-175)."""
         return torch.zeros(self._basis_parameters["linear_form_shape"], dtype=self.dtype, device=self.device)
 
-    def solve(self, matrix: torch.Tensor, solution: torch.Tensor, vector: torch.Tensor, only_inner_dofs: bool = True):
-        """Dense direct solve of the (reduced) system -- outside the assembly path (reference :177-195)."""
+    def solve(self, matrix: torch.Tensor, solution: torch.Tensor, vector: torch.Tensor, only_inner_dofs: bool = True,
+              rtol: float = 1e-10, max_iterations=None):
+        """Solve the (reduced) system and add the result to `solution` (reference :177-195).
+
+        Dense matrices take the reference's direct solve.  A CSR matrix too large to densify
+        (more than DENSE_LIMIT unknowns) is solved by preconditioned conjugate gradients on the
+        CSR arrays (`sparse.cg`, symmetric positive definite systems such as stiffness / mass);
+        the run's `sparse.CgInfo` is kept in `self.last_solve_info`."""
+        inner = self._basis_parameters["inner_dofs"]
+        if matrix.layout == torch.sparse_csr and matrix.shape[-1] > DENSE_LIMIT:
+            from .. import sparse
+
+            keep = None
+            if only_inner_dofs:
+                keep = torch.zeros(matrix.shape[-1], dtype=torch.uint8, device=matrix.device)
+                keep[inner] = 1
+            x, info = sparse.cg(matrix.crow_indices().to(torch.int32), matrix.col_indices().to(torch.int32), matrix.values(),
+                                vector, keep, rtol=rtol, max_iterations=max_iterations)
+            self.last_solve_info = info
+            if not info.converged:
+                raise RuntimeError(f"conjugate gradients stopped at relative residual {info.relative_residual:.3e} "
+                                   f"after {info.iterations} iterations")
+            if only_inner_dofs:
+                solution[inner] += x[inner].reshape(-1, 1)
+            else:
+                solution += x.reshape(solution.shape)
+            return solution
         if only_inner_dofs:
             matrix = self.reduce(matrix)
             vector = self.reduce(vector)
         elif matrix.layout == torch.sparse_csr:
             matrix = matrix.to_dense()
-        solution[self._basis_parameters["inner_dofs"]] += torch.linalg.solve(matrix, vector)
+        solution[inner] += torch.linalg.solve(matrix, vector)
         return solution
 
     # ------------------------------------------------------------------ subclass hooks

@@ -231,6 +231,21 @@ def unpack_add_raw(dst: Tensor, idx: Tensor, buf: Tensor) -> None:
     call("tfem_iface_unpack_add", dst.dtype, device, idx.shape[0], ptr(idx), ptr(buf), ptr(dst))
 
 
+@torch.library.custom_op(f"{NS}::csr_spmv", mutates_args=())
+def csr_spmv(crow: Tensor, col: Tensor, val: Tensor, x: Tensor, keep: Optional[Tensor] = None) -> Tensor:
+    """y = A x for the CSR matrix (crow, col, val); rows with keep == 0 (uint8) give 0."""
+    device = check_cuda(crow, col, val, x)
+    n_rows = crow.shape[0] - 1
+    y = torch.empty(n_rows, dtype=val.dtype, device=device)
+    call("tfem_csr_spmv", val.dtype, device, n_rows, ptr(crow), ptr(col), ptr(val), ptr(x), ptr(keep) if keep is not None else None, ptr(y))
+    return y
+
+
+@csr_spmv.register_fake
+def _(crow, col, val, x, keep=None):
+    return val.new_empty(crow.shape[0] - 1)
+
+
 # ------------------------------------------------------------------------------------------------
 # fused named forms
 # ------------------------------------------------------------------------------------------------

@@ -212,13 +212,23 @@ def edge_jump(grad_edges, normals, h_e, dx):
     return (h_e * (plus + minus) ** 2).unsqueeze(-1).mul(dx).sum(-1)
 
 
+def csr_spmv(crow, col, val, x, keep=None):
+    """Plain numpy restatement of y = A x with optional row mask (test stand-in for tfem_csr_spmv)."""
+    c, j, v = crow.numpy().astype(np.int64), col.numpy().astype(np.int64), val.numpy()
+    prod = v * x.numpy()[j]
+    y = np.add.reduceat(np.concatenate([prod, [0.0]]), np.minimum(c[:-1], prod.size)) * (c[1:] > c[:-1])
+    if keep is not None:
+        y = y * (keep.numpy() != 0)
+    return torch.from_numpy(np.asarray(y, dtype=v.dtype))
+
+
 def install(monkeypatch):
     """Route the op entry points to the oracle for one test (CPU host-logic checks only)."""
     from pytorch_fem_solver_b200.basis import abstract_basis
 
     monkeypatch.setattr(ops, "place_mesh", lambda mesh: mesh)
     for name in ("tri_geometry", "edge_geometry", "quad_reduce", "scatter", "gather", "unpack_add_", "local_forms",
-                 "weak_residual", "interp_cells", "interp_edges", "edge_jump", "assemble_csr_tiled"):
+                 "weak_residual", "interp_cells", "interp_edges", "edge_jump", "assemble_csr_tiled", "csr_spmv"):
         monkeypatch.setattr(ops, name, globals()[name])
 
     original = abstract_basis.AbstractBasis.tile_plan

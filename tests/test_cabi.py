@@ -48,3 +48,35 @@ def test_product_has_no_cpu_path():
     mesh = tfem.MeshTri(tfem.meshgen.structured_rectangle(2, 2))
     with pytest.raises(_lib.TfemError):
         tfem.Basis(mesh, tfem.ElementTri(1, 2))
+
+
+def _header_signatures():
+    """{base name: [C parameter type strings]} parsed from include/tfem_b200.h (macro and plain)."""
+    import re
+
+    with open(_lib.HEADER) as fh:
+        text = fh.read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S).replace("\\\n", " ")
+    found = {}
+    for match in re.finditer(r"(?:int|const char\*)\s+(tfem_\w+?)(_##SUF)?\s*\(([^)]*)\)\s*;", text):
+        name, _, params = match.groups()
+        params = [p.strip() for p in params.split(",") if p.strip() and p.strip() != "void"]
+        found[name] = params
+    return found
+
+
+def test_binding_arity_and_kinds_match_the_header():
+    """A ctypes argtypes list shorter than the C parameter list lets the extra argument through with the
+    default (32-bit int) conversion: pointers such as the stream then arrive truncated.  Every entry of
+    the binding tables must have exactly one argtype per C parameter, pointer for pointer."""
+    signatures = _header_signatures()
+    tables = {base: argtypes for base, argtypes in _lib._TYPED.items()}
+    tables.update({name: argtypes for name, (argtypes, _) in _lib._UNTYPED.items()})
+    assert set(tables) == set(signatures)
+    for name, params in signatures.items():
+        argtypes = tables[name]
+        assert len(argtypes) == len(params), f"{name}: {len(argtypes)} argtypes for {len(params)} C parameters"
+        for ctype, param in zip(argtypes, params):
+            is_pointer = "*" in param
+            bound_pointer = ctype in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ctype, "_type_") and isinstance(ctype._type_, type)
+            assert is_pointer == bool(bound_pointer), f"{name}: parameter '{param}' bound as {ctype}"

@@ -1,0 +1,116 @@
+"""Iterative solve on the assembled CSR system: host logic on CPU through the
+oracle-backed stand-ins, the real kernels under `-m gpu`."""
+
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse
+import scipy.sparse.linalg
+import torch
+
+import pytorch_fem_solver_b200 as tfem
+from pytorch_fem_solver_b200 import forms, meshgen, sparse
+from pytorch_fem_solver_b200.basis import abstract_basis
+from tests import cpu_shim
+
+
+def poisson_problem(device, nx, ny, jitter=0.2):
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        with torch.device(device):
+            mesh = tfem.MeshTri(meshgen.structured_rectangle(nx, ny, jitter=jitter, seed=5))
+            basis = tfem.Basis(mesh, tfem.ElementTri(1, 3))
+    finally:
+        torch.set_default_dtype(previous)
+    return basis
+
+
+def check_solve(device, nx, ny, monkeypatch=None):
+    """-Laplace u = 2 pi^2 sin(pi x) sin(pi y), u = 0 on the boundary: CG on the CSR system against
+    scipy's direct solve of the same reduced system, and against the analytic solution."""
+    basis = poisson_problem(device, nx, ny)
+    if monkeypatch is not None:
+        monkeypatch.setattr(abstract_basis, "DENSE_LIMIT", 16)  # force the CSR path on a small mesh
+    stiffness = basis.integrate_bilinear_form(forms.Stiffness())
+    load = basis.integrate_linear_form(forms.Load(forms.SinSinSource()))
+    assert stiffness.layout == torch.sparse_csr
+    if monkeypatch is None and stiffness.shape[0] <= abstract_basis.DENSE_LIMIT:
+        pytest.skip("mesh too small for the CSR solve path")
+    solution = basis.solve(stiffness, basis.solution_tensor(), load)
+    info = basis.last_solve_info
+    assert info.converged and info.relative_residual <= 1e-10
+    # same reduced system, direct
+    n = stiffness.shape[0]
+    a = scipy.sparse.csr_matrix((stiffness.values().cpu().numpy(), stiffness.col_indices().cpu().numpy(),
+                                 stiffness.crow_indices().cpu().numpy()), shape=(n, n))
+    inner = basis._basis_parameters["inner_dofs"].cpu().numpy()
+    direct = np.zeros(n)
+    direct[inner] = scipy.sparse.linalg.spsolve(a[inner][:, inner].tocsc(), load.cpu().numpy().reshape(-1)[inner])
+    ours = solution.cpu().numpy().reshape(-1)
+    assert np.abs(ours - direct).max() <= 1e-8 * np.abs(direct).max()
+    points = basis.mesh["vertices", "coordinates"].cpu().numpy().reshape(-1, 2)
+    exact = np.sin(math.pi * points[:, 0]) * np.sin(math.pi * points[:, 1])
+    h = 1.0 / min(nx, ny)
+    assert np.abs(ours - exact).max() < 3.0 * h * h  # O(h^2) nodal error of P1
+    return info
+
+
+def test_csr_diagonal_and_cg_small():
+    rng = np.random.default_rng(0)
+    m = scipy.sparse.random(40, 40, density=0.2, random_state=1, format="csr")
+    a = (m @ m.T + 40 * scipy.sparse.identity(40)).tocsr()
+    a.sort_indices()
+    crow, col = torch.from_numpy(a.indptr.astype(np.int32)), torch.from_numpy(a.indices.astype(np.int32))
+    val = torch.from_numpy(a.data)
+    assert np.allclose(sparse.csr_diagonal(crow, col, val).numpy(), a.diagonal())
+    b = torch.from_numpy(rng.standard_normal(40))
+    keep = torch.ones(40, dtype=torch.bool)
+    keep[[0, 7, 39]] = False
+    mp = pytest.MonkeyPatch()
+    try:
+        cpu_shim.install(mp)
+        x, info = sparse.cg(crow, col, val, b, keep, rtol=1e-12, check_every=5)
+    finally:
+        mp.undo()
+    assert info.converged
+    idx = np.nonzero(keep.numpy())[0]
+    ref = np.zeros(40)
+    ref[idx] = np.linalg.solve(a.toarray()[np.ix_(idx, idx)], b.numpy()[idx])
+    assert np.abs(x.numpy() - ref).max() < 1e-10
+
+
+def test_solve_csr_path_host_logic(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    check_solve("cpu", 24, 20, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_solve_small_forced_csr(monkeypatch):
+    check_solve("cuda", 24, 20, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_solve_quarter_million_unknowns():
+    info = check_solve("cuda", 512, 512)
+    assert info.iterations < 6000
+
+
+@pytest.mark.gpu
+def test_spmv_against_scipy_fp32_and_fp64():
+    from pytorch_fem_solver_b200 import ops
+
+    rng = np.random.default_rng(3)
+    a = scipy.sparse.random(3000, 3000, density=0.003, random_state=2, format="csr")
+    a.sort_indices()
+    for dtype, tol in ((np.float64, 1e-13), (np.float32, 2e-6)):
+        x = rng.standard_normal(3000).astype(dtype)
+        keep = rng.random(3000) < 0.8
+        args = [torch.from_numpy(a.indptr.astype(np.int32)).cuda(), torch.from_numpy(a.indices.astype(np.int32)).cuda(),
+                torch.from_numpy(a.data.astype(dtype)).cuda(), torch.from_numpy(x).cuda()]
+        y = ops.csr_spmv(*args).cpu().numpy()
+        ref = a.astype(np.float64) @ x.astype(np.float64)
+        assert np.abs(y - ref).max() <= tol * max(np.abs(ref).max(), 1.0)
+        y = ops.csr_spmv(*args, torch.from_numpy(keep.astype(np.uint8)).cuda()).cpu().numpy()
+        assert np.abs(y - ref * keep).max() <= tol * max(np.abs(ref).max(), 1.0)
