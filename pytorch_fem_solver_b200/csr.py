@@ -49,7 +49,7 @@ class CsrPattern:
         return out
 
     def to_sparse_csr(self, values: torch.Tensor) -> torch.Tensor:
-        return torch.sparse_csr_tensor(self.crow, self.col, values, size=(self.n_dof, self.n_dof))
+        return torch.sparse_csr_tensor(self.crow, self.col, values, size=(self.n_dof, self.n_dof), device=values.device)
 
 
 def coo_index_maps(dof_conn: torch.Tensor):

@@ -246,6 +246,13 @@ def _(crow, col, val, x, keep=None):
     return val.new_empty(crow.shape[0] - 1)
 
 
+def csr_spmv_raw(crow: Tensor, col: Tensor, val: Tensor, x: Tensor, keep: Optional[Tensor], out: Tensor) -> None:
+    """`csr_spmv` into a preallocated vector: direct C-ABI call for solver inner loops (CUDA-graph capturable)."""
+    device = check_cuda(crow, col, val, x, out)
+    call("tfem_csr_spmv", val.dtype, device, crow.shape[0] - 1, ptr(crow), ptr(col), ptr(val), ptr(x),
+         ptr(keep) if keep is not None else None, ptr(out))
+
+
 # ------------------------------------------------------------------------------------------------
 # fused named forms
 # ------------------------------------------------------------------------------------------------

@@ -47,11 +47,13 @@ def cg(
     rtol: float = 1e-10,
     max_iterations: Optional[int] = None,
     check_every: int = 50,
+    use_graph: bool = True,
 ):
     """Solve `(M A M) x = M rhs` for symmetric positive definite `M A M`, `M = diag(keep)`.
 
     crow/col int32, val/rhs float; keep bool/uint8 of length n or None (every row).  Returns
-    `(x, CgInfo)`; x is zero where keep is 0."""
+    `(x, CgInfo)`; x is zero where keep is 0.  On CUDA one iteration is captured in a CUDA graph
+    and replayed (`use_graph=False` keeps the eager loop)."""
     n = crow.shape[0] - 1
     b = rhs.reshape(-1).to(device=val.device, dtype=val.dtype)
     if b.shape[0] != n:
@@ -68,24 +70,49 @@ def cg(
     r = b - ops.csr_spmv(crow, col, val, x, keep8) if x0 is not None else b.clone()
     z = r * inv_diag
     p = z.clone()
-    rz = torch.dot(r, z)
+    ap = torch.empty_like(p)
+    rz = torch.dot(r, z).reshape(1)
     b_norm = float(torch.linalg.vector_norm(b))
     if b_norm == 0.0:
         return x, CgInfo(0, 0.0, True)
     limit = max_iterations if max_iterations is not None else 10 * n
-    iterations, rel = 0, float("inf")
     tiny = torch.finfo(val.dtype).tiny
-    while iterations < limit:
-        ap = ops.csr_spmv(crow, col, val, p, keep8)
+    spmv = getattr(ops, "csr_spmv_raw", None) if val.is_cuda else None
+
+    def iteration():  # every tensor it touches is preallocated: one CUDA graph replays it
+        if spmv is not None:
+            spmv(crow, col, val, p, keep8, ap)
+        else:
+            ap.copy_(ops.csr_spmv(crow, col, val, p, keep8))
         alpha = rz / torch.dot(p, ap).clamp_min(tiny)
         x.addcmul_(p, alpha)
         r.addcmul_(ap, alpha, value=-1.0)
-        z = r * inv_diag
-        rz_new = torch.dot(r, z)
+        torch.mul(r, inv_diag, out=z)
+        rz_new = torch.dot(r, z).reshape(1)
         p.mul_(rz_new / rz.clamp_min(tiny)).add_(z)
-        rz = rz_new
+        rz.copy_(rz_new)
+
+    step = iteration
+    iterations = 0
+    if val.is_cuda and use_graph:
+        # the loop is launch-bound (a dozen small kernels per iteration): capture one iteration
+        side = torch.cuda.Stream(device=val.device)
+        side.wait_stream(torch.cuda.current_stream(val.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm-up outside capture (allocator, lazy module loading)
+                iteration()
+            iterations = 3
+        torch.cuda.current_stream(val.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            iteration()
         iterations += 1
-        if iterations % check_every == 0 or iterations == limit:
+        step = graph.replay
+    rel = float("inf")
+    while iterations < limit:
+        step()
+        iterations += 1
+        if iterations % check_every == 0 or iterations >= limit:
             rel = float(torch.linalg.vector_norm(r)) / b_norm  # the only host synchronisation
             if rel <= rtol:
                 break
