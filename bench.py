@@ -148,6 +148,9 @@ def run_reference(args):
         return
     import torch
 
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm runs on rank 0 alone and may
+    # use every host core
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     # bounded sample of the same workload: a quarter-height strip keeps a step near one second
     nx, ny = args.nx, max(args.ny // 4, 1)
     from oracle.torch_cpu_port import reference_assembly_cpu

@@ -372,3 +372,43 @@ def test_progress_counter_releases_waiting_pack():
     assert torch.equal(outs[0], outs[1])
     crow_o, col_o, ref_vals, ref_load = oracle_system(mesh, 3, 0.7, 1.3)
     assert relmax(values.cpu().numpy(), ref_vals) < 1e-12 and relmax(load.cpu().numpy(), ref_load) < 1e-12
+
+
+def _irregular_meshes():
+    from tests.test_csr_symbolic import fan_mesh, nonmanifold_mesh
+
+    yield "delaunay200", meshgen.delaunay_unit_square(200, seed=4)
+    yield "permuted", meshgen.permute_mesh(meshgen.structured_rectangle(24, 24, jitter=0.2, topology=False))
+    yield "fan23", fan_mesh(23)  # one row with 23 elements: chained 7-element chunks
+    yield "nonmanifold", nonmanifold_mesh()  # entries with 3 contributions, a repeated vertex, an isolated vertex
+
+
+@pytest.mark.parametrize("name,mesh", list(_irregular_meshes()))
+@pytest.mark.parametrize("rows_per_tile", [8, 192])
+def test_tiled_kernel_on_irregular_meshes(name, mesh, rows_per_tile):
+    """The reduction phase's rarely taken paths (heavy entries, chunk links, short segments) against the
+    generic two-pass kernels and, where the elements are non-degenerate, the oracle."""
+    from pytorch_fem_solver_b200 import ops
+
+    mesh = {"vertices": np.asarray(mesh["vertices"], dtype=np.float64), "triangles": np.asarray(mesh["triangles"], dtype=np.int32),
+            "vertex_markers": np.ones((len(mesh["vertices"]), 1), dtype=np.int32)}
+    basis = make_basis(mesh, 3)
+    pat = basis.pattern
+    plan = basis.tile_plan(rows_per_tile)
+    src = forms.SinSinSource()
+    values = torch.full((pat.nnz,), float("nan"), dtype=torch.float64, device=DEV)
+    load = torch.full((pat.n_dof,), float("nan"), dtype=torch.float64, device=DEV)
+    ops.assemble_csr_tiled(plan.c_struct(), basis._layout.coords, 3, 0.7, 1.3, src.kind, src.params, values, load)
+    torch.cuda.synchronize()
+    ref_values, ref_load = basis.assemble(forms.StiffnessMass(0.7, 1.3), forms.Load(), layout="values", path="two_pass")
+    finite = torch.isfinite(ref_values)
+    assert torch.equal(torch.isfinite(values), finite)  # a degenerate element poisons the same entries in both paths
+    scale = float(ref_values[finite].abs().max())
+    assert float((values[finite] - ref_values[finite]).abs().max()) <= 1e-12 * scale
+    finite_l = torch.isfinite(ref_load.reshape(-1))
+    assert torch.equal(torch.isfinite(load), finite_l)
+    assert float((load[finite_l] - ref_load.reshape(-1)[finite_l]).abs().max()) <= 1e-12 * max(float(ref_load.reshape(-1)[finite_l].abs().max()), 1e-300)
+    if name != "nonmanifold":
+        crow, col, o_vals, o_load = oracle_system(mesh, 3, 0.7, 1.3)
+        assert np.array_equal(pat.crow.cpu().numpy(), crow) and np.array_equal(pat.col.cpu().numpy(), col)
+        assert relmax(values.cpu().numpy(), o_vals) < 1e-12 and relmax(load.cpu().numpy(), o_load) < 1e-12
