@@ -262,6 +262,12 @@ class AbstractBasis(abc.ABC):
             load_out.copy_(vec.reshape(load_out.shape), non_blocking=True)
         return values_out, load_out
 
+    def host_pipeline(self, bilinear, load, depth: int = 2) -> "HostPipeline":
+        """Stream of re-assemblies fed from / drained to HOST memory, `depth` steps in flight: the
+        host->device copy of step i+1, the assembly of step i and the device->host copy of step i-1 run
+        on three streams (PCIe is full duplex, so throughput is set by the larger copy alone)."""
+        return HostPipeline(self, bilinear, load, depth)
+
     def _assemble_fused(self, bilinear, source, path: str = "auto"):
         lay = self._layout
         pat = self.pattern
@@ -373,6 +379,64 @@ class AbstractBasis(abc.ABC):
     @abc.abstractmethod
     def _compute_basis_parameters(self, coords4global_dofs, global_dofs4elements, nodes4boundary_dofs) -> dict:
         raise NotImplementedError
+
+
+class HostPipeline:
+    """Double-buffered host -> assembly -> host pipeline of one basis (planar mesh, analytic source).
+
+    `step(coords_host, values_host, load_host)` enqueues one re-assembly for new vertex coordinates in
+    pinned host memory and returns immediately; results land in the given pinned host tensors in
+    submission order.  `synchronize()` waits for everything submitted.  The mesh topology, CSR
+    pattern and tile plan are those of the basis (nothing symbolic is redone)."""
+
+    def __init__(self, basis: "AbstractBasis", bilinear, load, depth: int = 2):
+        lay, pat = basis._layout, basis.pattern
+        src = forms.as_source(load.source if load is not None else None)
+        if lay.frac is not None or src.kind == ops.SRC_SAMPLED:
+            raise NotImplementedError("the host pipeline drives the tiled kernel: planar mesh and analytic source")
+        self.basis, self.depth = basis, max(int(depth), 1)
+        self.want_mat, self.want_vec = bilinear is not None, load is not None
+        self.alpha, self.beta = (bilinear.alpha, bilinear.beta) if self.want_mat else (0.0, 0.0)
+        self.src = src
+        self.order = basis._element.integration_order
+        self.plan = basis.tile_plan()
+        device, dtype = basis.device, basis.dtype
+        self.coords = [torch.empty_like(lay.coords) for _ in range(self.depth)]
+        self.values = [torch.empty(pat.nnz, dtype=dtype, device=device) if self.want_mat else None for _ in range(self.depth)]
+        self.load = [torch.empty(pat.n_dof, dtype=dtype, device=device) if self.want_vec else None for _ in range(self.depth)]
+        self.copy_in, self.compute, self.copy_out = (torch.cuda.Stream(device=device) for _ in range(3))
+        self.in_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.compute_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.out_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.submitted = 0
+
+    def step(self, coords_host: torch.Tensor, values_host: Optional[torch.Tensor], load_host: Optional[torch.Tensor]):
+        k = self.submitted % self.depth
+        recycled = self.submitted >= self.depth
+        with torch.cuda.stream(self.copy_in):
+            if recycled:
+                self.copy_in.wait_event(self.compute_done[k])  # the assembly that read this coordinate buffer
+            self.coords[k].copy_(coords_host.reshape(self.coords[k].shape), non_blocking=True)
+            self.in_done[k].record(self.copy_in)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.in_done[k])
+            if recycled:
+                self.compute.wait_event(self.out_done[k])  # the copy that drained these output buffers
+            ops.assemble_csr_tiled(self.plan.c_struct(), self.coords[k], self.order, self.alpha, self.beta,
+                                   self.src.kind if self.want_vec else 0, self.src.params, self.values[k], self.load[k])
+            self.compute_done[k].record(self.compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.compute_done[k])
+            if values_host is not None and self.want_mat:
+                values_host.copy_(self.values[k], non_blocking=True)
+            if load_host is not None and self.want_vec:
+                load_host.copy_(self.load[k].reshape(load_host.shape), non_blocking=True)
+            self.out_done[k].record(self.copy_out)
+        self.submitted += 1
+
+    def synchronize(self):
+        for stream in (self.copy_in, self.compute, self.copy_out):
+            stream.synchronize()
 
 
 class LazyParameters(dict):

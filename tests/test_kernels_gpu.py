@@ -412,3 +412,25 @@ def test_tiled_kernel_on_irregular_meshes(name, mesh, rows_per_tile):
         crow, col, o_vals, o_load = oracle_system(mesh, 3, 0.7, 1.3)
         assert np.array_equal(pat.crow.cpu().numpy(), crow) and np.array_equal(pat.col.cpu().numpy(), col)
         assert relmax(values.cpu().numpy(), o_vals) < 1e-12 and relmax(load.cpu().numpy(), o_load) < 1e-12
+
+
+def test_host_pipeline_matches_direct_assembly():
+    """Three streams, two steps in flight: every step's host outputs equal a plain assembly of that step's inputs."""
+    mesh = meshgen.structured_rectangle(64, 48, jitter=0.2, seed=21, topology=False)
+    basis = make_basis(mesh, 3)
+    pat = basis.pattern
+    bilinear, load = forms.StiffnessMass(0.7, 1.3), forms.Load(forms.SinSinSource())
+    rng = np.random.default_rng(5)
+    base = mesh["vertices"]
+    inputs = [torch.from_numpy(base + 1e-3 * rng.standard_normal(base.shape) * (i > 0)).pin_memory() for i in range(5)]
+    outs = [(torch.empty(pat.nnz, dtype=torch.float64).pin_memory(), torch.empty((pat.n_dof, 1), dtype=torch.float64).pin_memory()) for _ in inputs]
+    pipeline = basis.host_pipeline(bilinear, load, depth=2)
+    for coords, (values, vec) in zip(inputs, outs):
+        pipeline.step(coords, values, vec)
+    pipeline.synchronize()
+    for coords, (values, vec) in zip(inputs, outs):
+        ref_values, ref_vec = torch.empty_like(values), torch.empty_like(vec)
+        basis.assemble_from_host(coords, bilinear, load, ref_values, ref_vec, path="tiled")
+        torch.cuda.synchronize()
+        assert torch.equal(values, ref_values) and torch.equal(vec, ref_vec)
+    assert not torch.equal(outs[0][0], outs[1][0])  # the steps really had different inputs
