@@ -334,8 +334,10 @@ class PeerExchange:
 class StripAssembly:
     """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip.
 
-    `step()` assembles the tiles holding interface rows first, then the interior tiles on the main
-    stream while the interface exchange (pack -> NCCL send/recv -> add) runs on a side stream."""
+    `step()` is one persistent launch that walks the tiles holding interface rows first; the interface
+    exchange (pack into the owner's peer buffer -> signal -> add) runs on a side stream while the same
+    launch continues with the interior tiles.  With the collective transport (`TFEM_EXCHANGE=nccl`, gloo
+    tests) the interface and interior tiles are two launches and the exchange sits between them."""
 
     def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=192, group=None, exchange_ops=None):
         import numpy as np

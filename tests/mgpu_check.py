@@ -1,7 +1,7 @@
 """Multi-GPU parity check, run under torchrun with one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/mgpu_check.py [nx ny]
+        --master-port 29511 tests/mgpu_check.py [nx ny]
 
 Every rank assembles its strip with the tiled CUDA kernel, interface rows are exchanged over NCCL,
 and each rank compares its OWNED rows with the oracle's assembly of the whole (N-strip) mesh.
