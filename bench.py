@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--rows-per-tile", type=int, default=192)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--permuted", action="store_true",
+                   help="locality stress (SURVEY.md 8(d)): random renumbering of vertices and elements, default_rng(7); N=1 only")
     return p.parse_args()
 
 
@@ -67,7 +69,7 @@ def ncu_traffic(args):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json); only valid for the configuration that was profiled."""
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")
-    if args.path != "tiled" or (args.nx, args.ny) != (NX, NY) or not os.path.exists(path):
+    if args.path != "tiled" or (args.nx, args.ny) != (NX, NY) or args.permuted or args.rows_per_tile != 192 or not os.path.exists(path):
         return None
     with open(path) as fh:
         return json.load(fh).get("traffic_bytes_per_launch")
@@ -226,6 +228,8 @@ def run_ours(args):
 
     if world == 1:
         mesh_dict = tfem.meshgen.structured_rectangle(args.nx, args.ny, jitter=0.25, seed=1234, topology=False)
+        if args.permuted:
+            mesh_dict = tfem.meshgen.permute_mesh(mesh_dict, seed=7)
         with torch.device(device):
             basis = tfem.Basis(tfem.MeshTri(mesh_dict), tfem.ElementTri(1, QUAD_ORDER))
         assembler = None
@@ -236,14 +240,23 @@ def run_ours(args):
         basis = assembler.basis
         mesh_dict = assembler.mesh_dict
 
+    # one-time symbolic phase (CSR pattern: sort/unique of the COO keys; tile plan), timed separately
+    torch.cuda.synchronize()
+    t_symbolic = time.perf_counter()
     pat = basis.pattern
+    torch.cuda.synchronize()
+    symbolic_pattern_s = time.perf_counter() - t_symbolic
     lay = basis._layout
     n_el, n_v, nnz = lay.n_total, pat.n_dof, pat.nnz
     src = load_form.source
     values = torch.empty(nnz, dtype=torch.float64, device=device)
     load = torch.empty(n_v, dtype=torch.float64, device=device)
+    symbolic_plan_s = None
     if args.path == "tiled":
+        t_symbolic = time.perf_counter()
         plan = basis.tile_plan(args.rows_per_tile)
+        torch.cuda.synchronize()
+        symbolic_plan_s = time.perf_counter() - t_symbolic
         plan_struct = plan.c_struct()
 
         def local_step():
@@ -408,6 +421,10 @@ def run_ours(args):
                 "bytes_per_element": algorithmic / n_el,
             },
         }
+        line["config"]["symbolic_seconds"] = {"csr_pattern": round(symbolic_pattern_s, 3),
+                                              "tile_plan": None if symbolic_plan_s is None else round(symbolic_plan_s, 3)}
+        if args.permuted:
+            line["config"]["workload"] += "; vertices and elements randomly renumbered (default_rng(7)): locality stress, NOT the headline layout"
         if assembler is not None and args.path == "tiled":
             line["config"]["exchange"] = exchange_kind
         if plan is not None:
