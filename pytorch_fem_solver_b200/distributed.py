@@ -403,45 +403,94 @@ class StripAssembly:
                 print(f"[tfem] peer-memory exchange unavailable ({error!r}); using all_gather", file=sys.stderr)
         return FusedExchange(self.plan, nnz, self.basis.dtype, device, exchange_ops)
 
-    def _launch(self, plan, alpha, beta):
+    def _launch(self, plan, alpha, beta, coords=None, buffer=None):
         from . import ops
 
-        ops.assemble_csr_tiled(plan.c_struct(), self.basis._layout.coords, self.quad_order, alpha, beta,
-                               self.source.kind, self.source.params, self.values, self.load)
+        nnz = self.basis.pattern.nnz
+        buffer = self.buffer if buffer is None else buffer
+        ops.assemble_csr_tiled(plan.c_struct(), self.basis._layout.coords if coords is None else coords, self.quad_order,
+                               alpha, beta, self.source.kind, self.source.params, buffer[:nnz], buffer[nnz:])
 
-    def step(self, alpha: float = 1.0, beta: float = 1.0):
-        """One distributed assembly into `self.values` / `self.load` (owned rows complete)."""
+    def step(self, alpha: float = 1.0, beta: float = 1.0, coords: Optional[torch.Tensor] = None,
+             buffer: Optional[torch.Tensor] = None):
+        """One distributed assembly (owned rows complete) into `self.values` / `self.load`, or into
+        `buffer` = `[values | load]` from the vertex coordinates `coords` when given (host pipeline)."""
         main = torch.cuda.current_stream()
+        buffer = self.buffer if buffer is None else buffer
         if self._debug_no_exchange:  # profiling aid: the assembly launch alone (results incomplete on interface rows)
-            self._launch(self.ordered_tiles, alpha, beta)
+            self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
             return
         if self.single_launch:
             # ONE persistent launch walks the interface tiles first and counts them on a device
             # counter; the pack kernels on the side stream wait for that counter, store over NVLink
             # into the owners' buffers and signal, while the same launch goes on with the interior
             self.progress_target += self.n_interface_tiles * self.ordered_tiles.consumer_warps
-            self._launch(self.ordered_tiles, alpha, beta)
+            self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
             with torch.cuda.stream(self.side_stream):
                 self.side_stream.wait_event(self._previous_step)  # the buffer's previous contents are final
-                self.fused_exchange.pack(self.buffer, self.progress, self.progress_target)
-                self.fused_exchange.gather_add(self.buffer)
+                self.fused_exchange.pack(buffer, self.progress, self.progress_target)
+                self.fused_exchange.gather_add(buffer)
                 finished = torch.cuda.Event()
                 finished.record(self.side_stream)
             main.wait_event(finished)
             self._previous_step.record(main)
             return
-        self._launch(self.interface_tiles, alpha, beta)
+        self._launch(self.interface_tiles, alpha, beta, coords, buffer)
         ready = torch.cuda.Event()
         ready.record(main)
         # enqueue the long interior launch BEFORE the exchange so the GPU is busy while the host issues
         # the pack / exchange / add sequence on the side stream
-        self._launch(self.interior_tiles, alpha, beta)
+        self._launch(self.interior_tiles, alpha, beta, coords, buffer)
         with torch.cuda.stream(self.side_stream):
             self.side_stream.wait_event(ready)
-            self.fused_exchange(self.buffer)
+            self.fused_exchange(buffer)
             finished = torch.cuda.Event()
             finished.record(self.side_stream)
         main.wait_event(finished)
+
+
+class StripHostPipeline:
+    """`StripAssembly.step` fed from / drained to pinned HOST memory with `depth` steps in flight: the
+    host->device copy of step i+1, the distributed assembly of step i (launch + interface exchange) and
+    the device->host copy of step i-1 overlap on three streams (see basis.HostPipeline for one GPU)."""
+
+    def __init__(self, assembler: StripAssembly, depth: int = 2):
+        self.assembler, self.depth = assembler, max(int(depth), 1)
+        coords = assembler.basis._layout.coords
+        self.coords = [torch.empty_like(coords) for _ in range(self.depth)]
+        self.buffers = [torch.empty_like(assembler.buffer) for _ in range(self.depth)]
+        device = coords.device
+        self.copy_in, self.compute, self.copy_out = (torch.cuda.Stream(device=device) for _ in range(3))
+        self.in_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.compute_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.out_done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.submitted = 0
+        self.nnz = assembler.basis.pattern.nnz
+
+    def step(self, coords_host: torch.Tensor, values_host: torch.Tensor, load_host: torch.Tensor, alpha: float = 1.0, beta: float = 1.0):
+        k = self.submitted % self.depth
+        recycled = self.submitted >= self.depth
+        with torch.cuda.stream(self.copy_in):
+            if recycled:
+                self.copy_in.wait_event(self.compute_done[k])
+            self.coords[k].copy_(coords_host.reshape(self.coords[k].shape), non_blocking=True)
+            self.in_done[k].record(self.copy_in)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.in_done[k])
+            if recycled:
+                self.compute.wait_event(self.out_done[k])
+            self.assembler.step(alpha, beta, self.coords[k], self.buffers[k])
+            self.compute_done[k].record(self.compute)
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(self.compute_done[k])
+            values_host.copy_(self.buffers[k][: self.nnz], non_blocking=True)
+            load_host.copy_(self.buffers[k][self.nnz :].reshape(load_host.shape), non_blocking=True)
+            self.out_done[k].record(self.copy_out)
+        self.submitted += 1
+
+    def synchronize(self):
+        for stream in (self.copy_in, self.compute, self.copy_out):
+            stream.synchronize()
 
 
 def _basis_for(mesh, element):

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tests/mgpu_check.py [nx ny]
 
-Every rank assembles its strip with the tiled CUDA kernel, interface rows are exchanged over NCCL,
+Every rank assembles its strip with the tiled CUDA kernel, interface rows are exchanged (NCCL / NVLink peer memory),
 and each rank compares its OWNED rows with the oracle's assembly of the whole (N-strip) mesh.
 """
 
@@ -45,6 +45,15 @@ def main():
         asm.step()
     torch.cuda.synchronize()
     assert torch.equal(asm.values, values) and torch.equal(asm.load, load), "overlapped step differs from the serial one"
+    # the same steps fed from and drained to pinned host memory, two in flight
+    pipeline = distributed.StripHostPipeline(asm, depth=2)
+    coords_host = basis._layout.coords.cpu().pin_memory()
+    values_host = torch.empty(pat.nnz, dtype=torch.float64).pin_memory()
+    load_host = torch.empty((pat.n_dof, 1), dtype=torch.float64).pin_memory()
+    for _ in range(3):
+        pipeline.step(coords_host, values_host, load_host)
+    pipeline.synchronize()
+    assert torch.equal(values_host, values.cpu()) and torch.equal(load_host.reshape(-1), load.cpu()), "host pipeline differs"
 
     # oracle on the whole mesh (small sizes only)
     parts = [distributed.strip_mesh(nx, ny, r, world) for r in range(world)]
