@@ -254,7 +254,15 @@ int tfem_sm_count(void);
    * the matrix cannot be densified.  keep [n_rows] (0/1 bytes) or NULL: rows with keep == 0     \
    * (Dirichlet rows of AbstractBasis.reduce, abstract_basis.py:114-117) give y = 0. */          \
   int tfem_csr_spmv_##SUF(int64_t n_rows, const int32_t* crow, const int32_t* col, const T* val,   \
-                          const T* x, const uint8_t* keep, T* y, void* stream);
+                          const T* x, const uint8_t* keep, T* y, void* stream);                    \
+  /* One Jacobi-preconditioned conjugate-gradient iteration on (M A M) x = M b, M = diag(keep),   \
+   * as three launches with the dot products reduced in a fixed order (bitwise reproducible).    \
+   * State vectors x, r, z, p, ap [n]; inv_diag [n]; partial [2 * n_partial] scratch (n_partial  \
+   * = number of thread blocks used, e.g. 8 per SM); scal [2]: before the FIRST call set          \
+   * scal[1] = r.z (scal[0] is overwritten); after a call scal[1] holds the new r.z. */           \
+  int tfem_cg_iteration_##SUF(int64_t n, const int32_t* crow, const int32_t* col, const T* val,    \
+                              const uint8_t* keep, const T* inv_diag, T* x, T* r, T* z, T* p,      \
+                              T* ap, T* partial, int32_t n_partial, T* scal, void* stream);
 
 TFEM_DECLARE(double, f64)
 TFEM_DECLARE(float, f32)

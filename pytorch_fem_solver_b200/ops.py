@@ -253,6 +253,15 @@ def csr_spmv_raw(crow: Tensor, col: Tensor, val: Tensor, x: Tensor, keep: Option
          ptr(keep) if keep is not None else None, ptr(out))
 
 
+def cg_iteration_raw(crow: Tensor, col: Tensor, val: Tensor, keep: Optional[Tensor], inv_diag: Tensor, x: Tensor, r: Tensor,
+                     z: Tensor, p: Tensor, ap: Tensor, partial: Tensor, scal: Tensor) -> None:
+    """One fused preconditioned-CG iteration on preallocated state (see tfem_cg_iteration); CUDA-graph capturable."""
+    device = check_cuda(crow, col, val, inv_diag, x, r, z, p, ap, partial, scal)
+    call("tfem_cg_iteration", val.dtype, device, crow.shape[0] - 1, ptr(crow), ptr(col), ptr(val),
+         ptr(keep) if keep is not None else None, ptr(inv_diag), ptr(x), ptr(r), ptr(z), ptr(p), ptr(ap), ptr(partial),
+         partial.shape[0] // 2, ptr(scal))
+
+
 # ------------------------------------------------------------------------------------------------
 # fused named forms
 # ------------------------------------------------------------------------------------------------

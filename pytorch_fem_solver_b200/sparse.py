@@ -4,9 +4,9 @@ The reference solves `A[inner, inner] x = b[inner]` with a dense `torch.linalg.s
 (basis/abstract_basis.py:177-195), which cannot exist once the matrix is only representable as
 CSR (config 2: 2.1 M unknowns).  Here the same reduced system is solved by Jacobi-preconditioned
 conjugate gradients on the full-length vectors with the non-interior rows and columns masked out;
-the matrix-vector product is the hand-written `tfem_csr_spmv` kernel, everything else is a handful
-of stream-ordered vector updates with the scalars kept on the device (the host looks at the
-residual only every `check_every` iterations).
+one iteration is three hand-written kernels (`tfem_cg_iteration`: SpMV + p.Ap, the vector updates
++ r.z, the new direction) with every dot product reduced in a fixed order and the scalars kept on
+the device; the host looks at the residual only every `check_every` iterations.
 """
 
 from __future__ import annotations
@@ -48,12 +48,14 @@ def cg(
     max_iterations: Optional[int] = None,
     check_every: int = 50,
     use_graph: bool = True,
+    fused: bool = True,
 ):
     """Solve `(M A M) x = M rhs` for symmetric positive definite `M A M`, `M = diag(keep)`.
 
     crow/col int32, val/rhs float; keep bool/uint8 of length n or None (every row).  Returns
     `(x, CgInfo)`; x is zero where keep is 0.  On CUDA one iteration is captured in a CUDA graph
-    and replayed (`use_graph=False` keeps the eager loop)."""
+    and replayed (`use_graph=False` keeps the eager loop); `fused=False` uses torch vector
+    updates around `tfem_csr_spmv` instead of the three-kernel `tfem_cg_iteration`."""
     n = crow.shape[0] - 1
     b = rhs.reshape(-1).to(device=val.device, dtype=val.dtype)
     if b.shape[0] != n:
@@ -92,6 +94,17 @@ def cg(
         p.mul_(rz_new / rz.clamp_min(tiny)).add_(z)
         rz.copy_(rz_new)
 
+    fused_step = getattr(ops, "cg_iteration_raw", None) if (val.is_cuda and fused) else None
+    if fused_step is not None:
+        # three launches per iteration (tfem_cg_iteration): SpMV + p.Ap | x, r, z updates + r.z | new direction
+        blocks = 8 * torch.cuda.get_device_properties(val.device).multi_processor_count
+        partial = torch.zeros(2 * blocks, dtype=val.dtype, device=val.device)
+        scal = torch.cat([rz, rz]).contiguous()
+        inv_diag = inv_diag.contiguous()
+
+        def iteration():  # noqa: F811
+            fused_step(crow, col, val, keep8, inv_diag, x, r, z, p, ap, partial, scal)
+
     step = iteration
     iterations = 0
     if val.is_cuda and use_graph:
@@ -104,9 +117,8 @@ def cg(
             iterations = 3
         torch.cuda.current_stream(val.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph):  # records the launches, does not run them
             iteration()
-        iterations += 1
         step = graph.replay
     rel = float("inf")
     while iterations < limit:

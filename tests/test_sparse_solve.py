@@ -98,6 +98,26 @@ def test_solve_quarter_million_unknowns():
 
 
 @pytest.mark.gpu
+def test_fused_cg_matches_unfused_and_is_reproducible():
+    basis = poisson_problem("cuda", 96, 80)
+    stiffness = basis._matrix_result(basis._assemble_fused(forms.Stiffness(), None)[0], "csr")
+    load = basis.integrate_linear_form(forms.Load(forms.SinSinSource()))
+    keep = torch.zeros(stiffness.shape[0], dtype=torch.uint8, device="cuda")
+    keep[basis._basis_parameters["inner_dofs"]] = 1
+    args = (stiffness.crow_indices().to(torch.int32), stiffness.col_indices().to(torch.int32), stiffness.values(), load, keep)
+    x_fused, info = sparse.cg(*args, rtol=1e-11)
+    x_again, _ = sparse.cg(*args, rtol=1e-11)
+    x_plain, info_plain = sparse.cg(*args, rtol=1e-11, fused=False)
+    x_eager, _ = sparse.cg(*args, rtol=1e-11, use_graph=False)
+    assert info.converged and info_plain.converged
+    assert torch.equal(x_fused, x_again)  # fixed-order reductions: bitwise reproducible
+    assert torch.equal(x_fused, x_eager)  # graph replay == eager launches
+    scale = float(x_plain.abs().max())
+    assert float((x_fused - x_plain).abs().max()) <= 1e-8 * scale
+    assert float(x_fused[keep == 0].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
 def test_spmv_against_scipy_fp32_and_fp64():
     from pytorch_fem_solver_b200 import ops
 
