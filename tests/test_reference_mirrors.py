@@ -1,0 +1,126 @@
+"""Counterparts of the reference's own tests that are not golden-vector comparisons
+(SURVEY.md section 4): NN input derivatives vs finite differences, one embedded fracture == the planar
+problem, PatchesBasis on one patch == Basis on the same 5-vertex mesh.  CPU runs go through the
+oracle-backed stand-ins (host logic); `-m gpu` runs use the CUDA kernels."""
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_fem_solver_b200 as tfem
+from pytorch_fem_solver_b200 import forms, meshgen
+from tests import cpu_shim
+
+
+class BoundaryConstrain(torch.nn.Module):
+    def forward(self, inputs):
+        x, y = torch.split(inputs, 1, dim=-1)
+        return x * (x - 1) * y * (y - 1)
+
+
+def test_network_derivatives_match_finite_differences():
+    """reference tests/test_derivate_wrt_inputs.py:17-106 (fp64: atol 1e-8 / 1e-6 for the Laplacian)."""
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(0)
+        net = tfem.FeedForwardNeuralNetwork(2, 1, 4, 25, boundary_condition_modifier=BoundaryConstrain())
+        points = torch.rand(200, 4, 1, 2)  # any (.., q, 1, 2) set of points, as basis.integration_points
+        x, y = torch.split(points, 1, dim=-1)
+        h = 2.0**-9
+        grad = net.gradient(points.clone())
+        dx = (net(torch.cat([x + h, y], -1)) - net(torch.cat([x - h, y], -1))) / (2 * h)
+        dy = (net(torch.cat([x, y + h], -1)) - net(torch.cat([x, y - h], -1))) / (2 * h)
+        assert torch.allclose(dx, grad[..., :1], atol=1e-5) and torch.allclose(dy, grad[..., 1:], atol=1e-5)
+        lap = net.laplacian(points.clone())
+        d2x = (net(torch.cat([x + h, y], -1)) - 2 * net(points) + net(torch.cat([x - h, y], -1))) / h**2
+        d2y = (net(torch.cat([x, y + h], -1)) - 2 * net(points) + net(torch.cat([x, y - h], -1))) / h**2
+        assert torch.allclose(d2x + d2y, lap, atol=1e-4)
+    finally:
+        torch.set_default_dtype(previous)
+
+
+def one_fracture_equals_planar(device):
+    """reference tests/test_fracture_jump.py: a single fracture in the plane z = 0 reproduces the 2-D
+    basis: matrices, load, interpolants at the edge points, jump estimator."""
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        mesh_dict = meshgen.structured_rectangle(6, 5, jitter=0.2, seed=8, corners_first=True)
+        data = torch.tensor([[[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 1.0, 0.0]]])
+        with torch.device(device):
+            planar = tfem.MeshTri(mesh_dict)
+            basis2 = tfem.Basis(planar, tfem.ElementTri(1, 2))
+            edges2 = tfem.InteriorEdgesBasis(planar, tfem.ElementLine(1, 2))
+            embedded = tfem.FracturesTri([{k: v.copy() for k, v in mesh_dict.items()}], data.to(device))
+            basis3 = tfem.FractureBasis(embedded, tfem.ElementTri(1, 2))
+            edges3 = tfem.InteriorEdgesFractureBasis(embedded, tfem.ElementLine(1, 2))
+        # the fracture basis numbers its DOFs by the sorted 3-D vertices: local vertex i is global DOF to_global[i]
+        to_global = basis3.global_triangulation["global2local_idx"].reshape(-1).long()
+        a2 = basis2.integrate_bilinear_form(forms.StiffnessMass())
+        a3 = basis3.integrate_bilinear_form(forms.StiffnessMass())[to_global][:, to_global]
+        assert torch.allclose(a2, a3, rtol=1e-12, atol=1e-14)
+        source = lambda points: 1.0 + points[..., :1] * points[..., 1:2]  # noqa: E731
+        b2 = basis2.integrate_linear_form(forms.Load(source))
+        b3 = basis3.integrate_linear_form(forms.Load(source))[to_global]
+        assert torch.allclose(b2, b3, rtol=1e-12, atol=1e-15)
+        gen = torch.Generator().manual_seed(3)
+        u = torch.randn(b2.shape[0], 1, generator=gen, dtype=torch.float64).to(device)
+        v2, g2 = basis2.interpolate(edges2, u)
+        v3, g3 = basis3.interpolate(edges3, u)
+        assert torch.allclose(v2.reshape(-1), v3.reshape(-1), rtol=1e-12, atol=1e-14)
+        assert torch.allclose(g2.reshape(-1, 2), g3.reshape(-1, 3)[:, :2], rtol=1e-12, atol=1e-13)
+        assert float(g3.reshape(-1, 3)[:, 2].abs().max()) < 1e-13
+        eta2 = edges2.integrate_functional(forms.Jump(g2), planar["interior_edges", "normals"].unsqueeze(-2),
+                                           planar["interior_edges", "length"].unsqueeze(-2))
+        eta3 = edges3.integrate_functional(forms.Jump(g3), embedded["interior_edges", "normals_3d"].unsqueeze(-2),
+                                           embedded["interior_edges", "length"].unsqueeze(-2))
+        assert torch.allclose(eta2.reshape(-1), eta3.reshape(-1), rtol=1e-11, atol=1e-14)
+    finally:
+        torch.set_default_dtype(previous)
+
+
+def one_patch_equals_basis(device):
+    """reference tests/test_assembly_patches.py:1-74: PatchesBasis on the patch (centre .5,.5, r=.5) against Basis
+    on the same 5-vertex / 4-triangle mesh; also the known answers of SURVEY.md 8(c)."""
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        with torch.device(device):
+            patches = tfem.Patches(torch.tensor([[0.5, 0.5]]), torch.tensor([[0.5]]))
+            pbasis = tfem.PatchesBasis(patches, tfem.ElementTri(1, 2))
+            verts = patches["vertices", "coordinates"].reshape(5, 2).cpu().numpy()
+            cells = patches["cells", "vertices"].reshape(4, 3).cpu().numpy().astype(np.int32)
+            mesh = tfem.MeshTri({"vertices": verts, "triangles": cells, "vertex_markers": np.array([[1], [1], [1], [1], [0]], dtype=np.int32)})
+            basis = tfem.Basis(mesh, tfem.ElementTri(1, 2))
+        a_p = pbasis.integrate_bilinear_form(forms.Stiffness()).reshape(5, 5)
+        a_b = basis.integrate_bilinear_form(forms.Stiffness())
+        assert torch.allclose(a_p, a_b, rtol=1e-12, atol=1e-14)
+        expected = torch.tensor([[1.0, 0, 0, 0, -1], [0, 1, 0, 0, -1], [0, 0, 1, 0, -1], [0, 0, 0, 1, -1], [-1, -1, -1, -1, 4]])
+        assert torch.allclose(a_p.cpu(), expected, atol=1e-13)
+        b_p = pbasis.integrate_linear_form(forms.Load(forms.ConstSource(1.0))).reshape(5)
+        b_b = basis.integrate_linear_form(forms.Load(forms.ConstSource(1.0))).reshape(5)
+        assert torch.allclose(b_p, b_b, rtol=1e-12, atol=1e-15)
+        assert torch.allclose(b_p.cpu(), torch.tensor([1 / 6, 1 / 6, 1 / 6, 1 / 6, 1 / 3]), atol=1e-14)
+    finally:
+        torch.set_default_dtype(previous)
+
+
+def test_one_fracture_equals_planar_host_logic(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    one_fracture_equals_planar("cpu")
+
+
+def test_one_patch_equals_basis_host_logic(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    one_patch_equals_basis("cpu")
+
+
+@pytest.mark.gpu
+def test_one_fracture_equals_planar_gpu():
+    one_fracture_equals_planar("cuda")
+
+
+@pytest.mark.gpu
+def test_one_patch_equals_basis_gpu():
+    one_patch_equals_basis("cuda")
