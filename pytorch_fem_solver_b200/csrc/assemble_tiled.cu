@@ -43,6 +43,9 @@
 #ifndef TFEM_MIN_CTAS
 #define TFEM_MIN_CTAS 3  // resident CTAs per SM of the 256-consumer build (caps registers at 72)
 #endif
+#ifndef TFEM_LIGHT_UNROLL
+#define TFEM_LIGHT_UNROLL 2  // segments a warp keeps in flight in the reduction phase
+#endif
 #ifndef TFEM_MIN_CTAS_128
 #define TFEM_MIN_CTAS_128 5
 #endif
@@ -517,7 +520,8 @@ __global__ void __launch_bounds__(CONSUMERS + 32, (CONSUMERS == 128 ? TFEM_MIN_C
       // and no inner loop.
       // Runs are cut into segments of <= 32 entries, one warp pass each.
       const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll 2
+      constexpr int kLightUnroll = TFEM_LIGHT_UNROLL;
+#pragma unroll kLightUnroll
       for (int sg = warp; sg < ((TFEM_DEBUG_SKIP & 4) ? 0 : ev.n_runs); sg += kWarps) {
         const uint32_t meta = (uint32_t)lv.run_meta[sg];
         if (lane < (int)(meta >> 16)) {
