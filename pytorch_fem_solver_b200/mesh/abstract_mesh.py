@@ -16,7 +16,7 @@ Mirrors the key layout and shapes of the reference's `AbstractMesh`
 from __future__ import annotations
 
 import abc
-from typing import Any, Tuple
+from typing import Any
 
 import numpy as np
 import torch

@@ -1,11 +1,9 @@
 """Parity of the CUDA path (through the C ABI and the custom ops) with the reference's golden
 outputs and with the oracle.  Needs a GPU: `pytest -m gpu`."""
 
-import numpy as np
 import pytest
 import torch
 
-from oracle import fem_oracle as fo
 from tests import api_checks
 
 pytestmark = pytest.mark.gpu

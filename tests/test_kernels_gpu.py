@@ -1,7 +1,6 @@
 """Kernel-level parity on the GPU against the oracle: precisions, edge cases, determinism and
 size-independent properties at the full BASELINE config-2 size.  `pytest -m gpu`."""
 
-import math
 
 import numpy as np
 import pytest
