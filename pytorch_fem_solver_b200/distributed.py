@@ -389,6 +389,8 @@ class StripAssembly:
         self._previous_step = torch.cuda.Event() if self.side_stream is not None else None
         if self._previous_step is not None:
             self._previous_step.record(torch.cuda.current_stream())
+        # ranks leave set-up together: the first step's device-side waits (bounded) then only see kernel-scale skew
+        dist.barrier(group=self.plan.group)
 
     def _make_exchange(self, nnz, device, exchange_ops):
         """Peer-memory stores + signals on NVLink when the ranks are CUDA peers (TFEM_EXCHANGE=peer, the
