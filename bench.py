@@ -413,7 +413,7 @@ def run_ours(args):
                 "traffic": ncu_traffic(args),
                 "peak_source": peak_source,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel": "assemble_tiled_kernel<double,256,true,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
+                "kernel": "assemble_tiled_kernel<double,256,3,SINSIN,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algorithmic,
                 "bytes_per_element": algorithmic / n_el,
