@@ -324,6 +324,25 @@ def assemble_csr_tiled(plan, coords: Tensor, quad_order: int, alpha: float, beta
 # ------------------------------------------------------------------------------------------------
 
 
+def _weak_residual_local_launch(grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind,
+                                source_p, f_q, frac_jac, frac_inv, frac_det, frac_t) -> Tensor:
+    """The launch itself (shared by the stand-alone op and by `weak_residual`, which would otherwise pay a
+    second custom-op dispatch per training step)."""
+    device = check_cuda(grad_u, coords, conn, dof_conn, f_q, frac_jac, frac_inv, frac_det, frac_t)
+    n_q = _nq_tri(quad_order)
+    n_el = conn.shape[0]
+    d = 3 if frac_inv is not None else 2
+    if tuple(grad_u.shape) != (n_el, n_q, d):
+        raise TfemError(f"grad_u must have shape {(n_el, n_q, d)}, got {tuple(grad_u.shape)}")
+    out = torch.empty((n_el, 3), dtype=coords.dtype, device=device)
+    src = make_source(source_kind, source_p)
+    call(
+        "tfem_weak_residual_local", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+        quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(frac_t), src, ptr(f_q), ptr(grad_u), ptr(out),
+    )
+    return out
+
+
 @torch.library.custom_op(f"{NS}::weak_residual_local", mutates_args=())
 def weak_residual_local(
     grad_u: Tensor,
@@ -342,19 +361,8 @@ def weak_residual_local(
     frac_t: Optional[Tensor] = None,
 ) -> Tensor:
     """grad_u (N,q,d) -> per-element residual (N,3): sum_q dx (f phi_i - grad phi_i . grad_u)."""
-    device = check_cuda(grad_u, coords, conn, dof_conn, f_q, frac_jac, frac_inv, frac_det, frac_t)
-    n_q = _nq_tri(quad_order)
-    n_el = conn.shape[0]
-    d = 3 if frac_inv is not None else 2
-    if tuple(grad_u.shape) != (n_el, n_q, d):
-        raise TfemError(f"grad_u must have shape {(n_el, n_q, d)}, got {tuple(grad_u.shape)}")
-    out = torch.empty((n_el, 3), dtype=coords.dtype, device=device)
-    src = make_source(source_kind, source_p)
-    call(
-        "tfem_weak_residual_local", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
-        quad_order, ptr(frac_jac), ptr(frac_inv), ptr(frac_det), ptr(frac_t), src, ptr(f_q), ptr(grad_u), ptr(out),
-    )
-    return out
+    return _weak_residual_local_launch(grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order,
+                                       source_kind, source_p, f_q, frac_jac, frac_inv, frac_det, frac_t)
 
 
 @weak_residual_local.register_fake
@@ -415,7 +423,7 @@ def weak_residual(
     frac_t: Optional[Tensor] = None,
 ) -> Tensor:
     """Global weak residual r (n_dof,): element kernel + deterministic scatter, two launches."""
-    local = weak_residual_local(
+    local = _weak_residual_local_launch(
         grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind, source_p,
         f_q, frac_jac, frac_inv, frac_det, frac_t,
     )
