@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
+import sys
 import threading
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint32, c_void_p
 
@@ -120,6 +121,15 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and "TFEM_B200_LIB" not in os.environ:
+        # a fresh checkout: compile the CUDA library once (nvcc, sm_100a).  This is the product path
+        # itself, not a fallback; if it cannot be built the error below stands.
+        try:
+            from . import build
+
+            build.build()
+        except Exception as error:  # noqa: BLE001 - reported, then the hard failure below
+            print(f"[tfem] building {LIB_PATH} failed: {error!r}", file=sys.stderr)
     if not os.path.exists(LIB_PATH):
         raise TfemError(
             f"{LIB_PATH} is missing: build it with `python -m pytorch_fem_solver_b200.build` "
