@@ -118,7 +118,7 @@ typedef struct tfem_tile_plan {
   const int32_t* lb_off; /* [n_tiles+1] word offset of each tile's LB blob, multiples of 4 */
   const int32_t* lb_blob;
   int32_t max_vert, max_elem, max_e_words, max_la_words, max_lb_words; /* per-tile maxima (shared-memory sizing) */
-  int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = choose from max_elem */
+  int32_t consumer_threads; /* 128, 192, 256, 384 or 512 compute threads per CTA; 0 = library default (256) */
   int32_t elem_stride;      /* row length of the local-matrix table, > max_elem (last column = zeros), multiple of 32 */
   int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
                                (interface pack / signal / add) can run beside it; 0 = use every slot */
