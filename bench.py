@@ -48,7 +48,7 @@ def parse_args():
     p.add_argument("--nx", type=int, default=NX)
     p.add_argument("--ny", type=int, default=NY)
     p.add_argument("--path", default="tiled", choices=["tiled", "two_pass"])
-    p.add_argument("--rows-per-tile", type=int, default=192)
+    p.add_argument("--rows-per-tile", type=int, default=336)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--permuted", action="store_true",
@@ -68,7 +68,7 @@ def ncu_traffic(args):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/roofline_traffic.json); only valid for the configuration that was profiled."""
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")
-    if args.path != "tiled" or (args.nx, args.ny) != (NX, NY) or args.permuted or args.rows_per_tile != 192 or not os.path.exists(path):
+    if args.path != "tiled" or (args.nx, args.ny) != (NX, NY) or args.permuted or args.rows_per_tile != 336 or not os.path.exists(path):
         return None
     with open(path) as fh:
         return json.load(fh).get("traffic_bytes_per_launch")
@@ -413,7 +413,7 @@ def run_ours(args):
                 "traffic": ncu_traffic(args),
                 "peak_source": peak_source,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel": "assemble_tiled_kernel<double,256,3,SINSIN,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
+                "kernel": "assemble_tiled_kernel<double,384,3,SINSIN,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algorithmic,
                 "bytes_per_element": algorithmic / n_el,
@@ -427,7 +427,8 @@ def run_ours(args):
             line["config"]["exchange"] = exchange_kind
         if plan is not None:
             line["config"]["tile_plan"] = {"tiles": plan.n_tiles, "rows_per_tile": args.rows_per_tile, "halo_factor": round(plan.halo_factor, 4),
-                                           "index_bytes": plan.index_bytes, "max_vert": plan.max_vert, "max_elem": plan.max_elem, "max_out": plan.max_out}
+                                           "index_bytes": plan.index_bytes, "max_vert": plan.max_vert, "max_elem": plan.max_elem, "templates": plan.n_templates,
+                                           "lattice": plan.lattice}
         if e2e:
             line["e2e"] = {
                 "value": total_elements / e2e_step_s,

@@ -64,62 +64,60 @@ typedef struct tfem_bilinear {
   double beta;  /* mass coefficient      */
 } tfem_bilinear;
 
-/* Tile plan of the fused assembly kernel (all pointers DEVICE memory, built once per mesh by
+/* Tile plan (format v2) of the fused assembly kernel (all pointers DEVICE memory, built once per mesh by
  * pytorch_fem_solver_b200/tileplan.py; see DESIGN.md "tile plan").
- * A tile owns a set of CSR rows; its elements are all elements touching those rows.  Per tile there
- * are three blobs of 32-bit words, each 16 B aligned and a whole number of 16 B units so that one TMA
- * bulk copy fetches it; every section is padded to a multiple of 4 words; 16- and 8-bit sections
- * are packed little-endian.
+ * A tile owns a set of CSR rows; its elements are all elements touching those rows.  The index data of
+ * a tile are split into a TEMPLATE -- the tile-local structure, which depends on the mesh topology
+ * around the tile only and is shared by all congruent tiles (every interior tile of a lattice-numbered
+ * mesh) -- and a small per-tile INSTANCE.  Blobs are 32-bit words, 16 B aligned and whole 16 B units so
+ * that one TMA bulk copy fetches each; every section is padded to a multiple of 4 words; 16-bit
+ * sections are packed little-endian.
  *
- *   E blob ("early": producer warp + integration phase)
- *     header[12]       n_vert, n_elem, n_rows, n_runs, n_out, n_chunks, base_vertex, n_heavy_contrib,
- *                      n_heavy, 0, 0, 0
- *                      (base_vertex: row of `coords` of a vertex near the middle of the tile; the
- *                      source's sin/cos are evaluated once there and rotated to the other vertices)
+ *   instance blob (one per tile)
+ *     header[4]        n_vert, n_segs, n_rows, base_vertex (tile-local index of a vertex near the middle
+ *                      of the tile: the source's sin/cos are evaluated once there and rotated to the
+ *                      centroid of every tile element)
  *     vert[n_vert]     u32  row of `coords` of each tile-local vertex
+ *     seg_start[n_segs] u32 csr_val offset of the first entry of each segment: a run of consecutive CSR
+ *                      rows cut into pieces of at most 32 entries (one warp pass each)
+ *     row_id[n_rows]   u32  global row (DOF) of each owned row, ascending
+ *   template, part TB (integration phase)
+ *     header[8]        n_vert, n_elem, n_rows, n_segs, n_chunks, n_heavy, n_heavy_contrib, 0
  *     elem[n_elem]     u32  tile-local connectivity  v0 | v1<<10 | v2<<20
- *   LA blob ("late", entries: first half of the reduction phase)
- *     run_start[n_runs]    u32  CSR offset of the first entry of a segment: a run of consecutive rows
- *                               cut into pieces of at most 32 entries (one warp pass each)
- *     run_meta[n_runs]     u32  image offset of the segment | length<<16
- *     pair[n_out]          u32  one word per CSR entry of the tile; entries are numbered run after run
- *                               ("image order"), so entry o of run r sits at
- *                               csr_val[run_start[r] + o - image offset of r].  lo 16 bits = first,
- *                               hi 16 bits = second contribution, each a code
- *                               slot*elem_stride + tile element (slot 0..5 = K00 K11 K22 K01 K12 K20),
- *                               i.e. a direct index into the CTA's local-matrix table, in increasing
- *                               element id (the summation order of the reference's index_put_/coalesce);
- *                               an absent contribution is the code elem_stride-1 (a column of zeros);
- *                               0xFFFFFFFF = entry summed elsewhere (row_diag or the heavy list)
+ *   template, part TC (reduction phase)
+ *     pair[n_segs][32]     u32  one word per lane of each segment: lane l of segment s owns
+ *                               csr_val[seg_start[s] + l].  lo 16 bits = first, hi 16 bits = second
+ *                               contribution, each a code (tile element + 1) * 9 + slot (slot 0..5 =
+ *                               K00 K11 K22 K01 K12 K20, 6..8 = load), i.e. a direct index into the
+ *                               CTA's local table [1 + n_elem][9] whose row 0 holds zeros (code 0 =
+ *                               "no contribution"), in increasing element id (the summation order of
+ *                               the reference's index_put_/coalesce); 0xFFFFFFFF = lane without an
+ *                               entry, or entry summed elsewhere (row_diag or the heavy list)
+ *     row_chunk[n_chunks][8] u16  chunk j < n_rows belongs to owned row j: 7 codes
+ *                               (tile element + 1) * 9 + k (k = local vertex) of the elements around
+ *                               the row's vertex, padded with 0; the code indexes the row's diagonal
+ *                               term, its load term sits 6 slots further; the 8th value is the index of
+ *                               the row's next chunk (rows with more than 7 elements), 0 = none
+ *     row_diag[n_rows]     u16  entry code (segment * 32 + lane) of the row's diagonal when the row's
+ *                               thread sums it (same element list as the load entry), else 0xFFFF
  *     heavy_seg[n_heavy+1] u16  offsets into heavy_contrib[] of the other entries with more than two
  *                               contributions (non-manifold edges, degenerate elements)
  *     heavy_contrib[n_heavy_contrib] u16  their codes
- *     heavy_pos[n_heavy]   u32  their csr_val positions
- *   LB blob ("late", rows: second half of the reduction phase)
- *     row_id[n_rows]       u32  global row (DOF) of each owned row, ascending
- *     row_chunk[n_chunks][8] u16  chunk j < n_rows belongs to owned row j: 7 codes
- *                               k*elem_stride + tile element (k = local vertex) of the elements around
- *                               the row's vertex, padded with elem_stride-1; the code indexes the row's
- *                               diagonal term, its load term sits 6*elem_stride further; the 8th value
- *                               is the index of the row's next chunk (rows with more than 7 elements),
- *                               0 = none
- *     row_diag[n_rows]     u32  csr_val position of the row's diagonal when the row's thread sums it
- *                               (same element list as the load entry), else 0xFFFFFFFF
- *   The LA buffer of a CTA is refilled as soon as its warps are through the entries of the previous
- *   tile, the LB buffer once the previous tile is finished.                                           */
+ *     heavy_pos[n_heavy]   u16  their entry codes (segment * 32 + lane)
+ *   A CTA keeps ONE template resident in shared memory; TB is refetched after the integration phase of
+ *   the previous tile and TC after its reduction phase, only when the template changes.               */
 typedef struct tfem_tile_plan {
-  int64_t n_tiles;          /* tiles this call processes */
-  const int32_t* tile_list; /* [n_tiles] ids of those tiles, or NULL for tiles 0..n_tiles-1; lets one plan be
-                               run in parts (interface tiles first, interior tiles while the exchange runs) */
-  const int32_t* e_off;  /* [n_tiles+1] word offset of each tile's E blob, multiples of 4 */
-  const int32_t* e_blob;
-  const int32_t* la_off; /* [n_tiles+1] word offset of each tile's LA blob, multiples of 4 */
-  const int32_t* la_blob;
-  const int32_t* lb_off; /* [n_tiles+1] word offset of each tile's LB blob, multiples of 4 */
-  const int32_t* lb_blob;
-  int32_t max_vert, max_elem, max_e_words, max_la_words, max_lb_words; /* per-tile maxima (shared-memory sizing) */
-  int32_t consumer_threads; /* 128, 192, 256, 384 or 512 compute threads per CTA; 0 = library default (256) */
-  int32_t elem_stride;      /* row length of the local-matrix table, > max_elem (last column = zeros), multiple of 32 */
+  int64_t n_tiles;           /* tiles this call processes (length of tile_list) */
+  const int32_t* tile_list;  /* [n_tiles] ids of those tiles, in processing order (congruent tiles adjacent); lets one
+                                plan be run in parts (interface tiles first, interior tiles while the exchange runs).
+                                The first n_progress_tiles are dealt round-robin over the CTAs, the rest in contiguous
+                                blocks (one per CTA), so that a CTA rarely changes template */
+  const int32_t* tile_desc;  /* [all tiles][4]: instance word offset, instance words, template id, 0 */
+  const int32_t* inst_blob;
+  const int32_t* tpl_desc;   /* [templates][4]: TB word offset, TB words, TC word offset, TC words */
+  const int32_t* tpl_blob;
+  int32_t max_vert, max_elem, max_inst_words, max_tb_words, max_tc_words; /* per-tile maxima (shared-memory sizing) */
+  int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = library default (384) */
   int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
                                (interface pack / signal / add) can run beside it; 0 = use every slot */
   int32_t n_progress_tiles; /* the first n_progress_tiles tiles of the call (in tile_list order) report on

@@ -46,19 +46,16 @@ class TilePlan(Structure):
     _fields_ = [
         ("n_tiles", c_int64),
         ("tile_list", c_void_p),
-        ("e_off", c_void_p),
-        ("e_blob", c_void_p),
-        ("la_off", c_void_p),
-        ("la_blob", c_void_p),
-        ("lb_off", c_void_p),
-        ("lb_blob", c_void_p),
+        ("tile_desc", c_void_p),
+        ("inst_blob", c_void_p),
+        ("tpl_desc", c_void_p),
+        ("tpl_blob", c_void_p),
         ("max_vert", c_int32),
         ("max_elem", c_int32),
-        ("max_e_words", c_int32),
-        ("max_la_words", c_int32),
-        ("max_lb_words", c_int32),
+        ("max_inst_words", c_int32),
+        ("max_tb_words", c_int32),
+        ("max_tc_words", c_int32),
         ("consumer_threads", c_int32),
-        ("elem_stride", c_int32),
         ("reserve_ctas", c_int32),
         ("n_progress_tiles", c_int32),
         ("progress", c_void_p),

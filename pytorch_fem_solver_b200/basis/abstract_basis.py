@@ -152,7 +152,7 @@ class AbstractBasis(abc.ABC):
             self._scatter_inverse[kind] = inverse
         return self._scatter_inverse[kind]
 
-    def tile_plan(self, rows_per_tile: int = 192, ordering: str = "block"):
+    def tile_plan(self, rows_per_tile: int = 336, ordering: str = "auto"):
         """Row-tile plan of the fused assembly kernel (planar meshes), cached per setting."""
         key = (rows_per_tile, ordering)
         if key not in self._tile_plans:

@@ -339,7 +339,7 @@ class StripAssembly:
     launch continues with the interior tiles.  With the collective transport (`TFEM_EXCHANGE=nccl`, gloo
     tests) the interface and interior tiles are two launches and the exchange sits between them."""
 
-    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=192, group=None, exchange_ops=None):
+    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=336, group=None, exchange_ops=None):
         import numpy as np
 
         from . import ElementTri, MeshTri, forms

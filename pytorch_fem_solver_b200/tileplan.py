@@ -1,21 +1,23 @@
-"""Row-tile plan of the fused assembly kernel (`tfem_tri_p1_assemble_csr`).
+"""Row-tile plan of the fused assembly kernel (`tfem_tri_p1_assemble_csr`), format v2.
 
-Integer, one-time set-up in torch (any device).  CSR rows are clustered into tiles; for every tile
-three packed, 16 B-aligned blobs are produced (layouts in include/tfem_b200.h):
+Integer, one-time set-up in torch (any device).  CSR rows are clustered into tiles; a tile's elements
+are all elements touching its rows.  Everything the kernel needs per tile is split in two:
 
-  E ("early")  what the producer warp and the integration phase need: header, the tile's
-               vertices (rows of `coords`) and its tile-local connectivity;
-  LA ("late", entries)  segments of consecutive CSR slots and for every CSR entry of the tile ONE
-               word holding its (at most two) contributions as (local-matrix slot, element)
-               codes in increasing element order;
-  LB ("late", rows)  owned row ids and for every row fixed-size chunks listing the elements of
-               its load / diagonal entry.
+  template  the tile-LOCAL index structure, which depends on the mesh topology around the tile only:
+            tile-local connectivity (TB blob) and, for every CSR entry / row of the tile, which local
+            (element, slot) contributions it sums (TC blob).  Congruent tiles -- every interior tile of
+            a lattice-numbered mesh -- share ONE template; the kernel keeps it resident in shared
+            memory and refetches only when consecutive tiles differ.
+  instance  what is specific to a tile: the rows of `coords` of its vertices, the global CSR offset
+            of each of its entry segments and its global row ids (one small blob per tile).
 
-Each blob is fetched by one TMA bulk copy, so per-tile sections are padded to whole 16 B units.
+Layouts are documented in include/tfem_b200.h.  Every blob is fetched by one TMA bulk copy, so sections
+are padded to whole 16 B units.
 """
 
 from __future__ import annotations
 
+import dataclasses
 import os
 from dataclasses import dataclass
 
@@ -24,7 +26,14 @@ import torch
 from . import _lib
 from .csr import CsrPattern
 
-HEADER_WORDS = 12
+INST_HEADER_WORDS = 4
+TB_HEADER_WORDS = 8
+SEG = 32  # entries per segment: one warp pass, one lane per entry
+PER_CHUNK = 7  # contribution codes per 16 B row chunk (+ link)
+N_SLOTS = 9  # K00 K11 K22 K01 K12 K20 b0 b1 b2
+MAX_VERT = 1024  # 10-bit tile-local vertex ids
+MAX_ELEM = 7000  # 16-bit codes (element + 1) * 9 + slot
+MAX_SEGS = 2047  # 16-bit entry codes seg * 32 + lane, 0xFFFF = none
 
 
 def _spread_bits16(v: torch.Tensor) -> torch.Tensor:
@@ -64,6 +73,50 @@ def block_tiles(points: torch.Tensor, rows_per_tile: int):
     return tile_of_point, int(used.shape[0]), int(counts.max().item())
 
 
+def detect_lattice(pattern: CsrPattern):
+    """Row stride W of a lattice-numbered mesh (DOF id = j*W + i), read off the CSR pattern alone.
+
+    The commonest column-offset signature of the 7-entry rows of a structured triangulation is
+    (-W-1, -W, -1, 0, 1, W, W+1) or (-W, -W+1, -1, 0, 1, W-1, W).  Returns W, or 0 when fewer than
+    half of the rows follow one such stencil or the numbering does not wrap consistently.  Tiles of
+    such a mesh are cut in INDEX space, so they do not depend on vertex positions (jittered vertices
+    leave every interior tile congruent, which is what lets the templates be shared)."""
+    n = pattern.n_dof
+    if n < 16 or pattern.nnz < 7 * 8:
+        return 0
+    crow = pattern.crow.long()
+    length = crow[1:] - crow[:-1]
+    rows7 = torch.nonzero(length == 7, as_tuple=True)[0]
+    if rows7.numel() * 2 < n:
+        return 0
+    sample = rows7[:: max(rows7.numel() // 4096, 1)]
+    offs = pattern.col.long()[crow[sample][:, None] + torch.arange(7, device=crow.device)[None, :]] - sample[:, None]
+    signatures, counts = torch.unique(offs, dim=0, return_counts=True)
+    best = signatures[int(torch.argmax(counts))].tolist()
+    if int(counts.max()) * 2 < sample.numel():
+        return 0
+    if best[2:5] != [-1, 0, 1] or best[0] != -best[6] or best[1] != -best[5] or best[6] - best[5] != 1:
+        return 0
+    col = pattern.col.long()
+    row_of = pattern.row_indices()
+    has_next = torch.zeros(n, dtype=torch.bool, device=crow.device)
+    has_next[row_of[col == row_of + 1]] = True
+    for width in (best[5], best[6]):
+        if width < 2 or n % width != 0:
+            continue
+        last_in_row = (torch.arange(n, device=crow.device) % width) == width - 1
+        if not bool((has_next & last_in_row).any()) and bool(has_next[~last_in_row].all()):
+            return int(width)
+    return 0
+
+
+def lattice_shape(rows_per_tile: int):
+    """(bx, by): tile extent in lattice columns / lattice rows for about `rows_per_tile` rows."""
+    by = max(int(round((rows_per_tile / 1.3) ** 0.5)), 1)
+    bx = max(rows_per_tile // by, 1)
+    return bx, by
+
+
 def _pad4(t):
     return (t + 3) & ~3
 
@@ -87,15 +140,18 @@ def _wrap_u32(t: torch.Tensor) -> torch.Tensor:
 @dataclass
 class _Section:
     name: str
-    bits: int  # 32, 16 or 8
+    bits: int  # 32 or 16
     count: torch.Tensor  # (n_tiles,) items per tile
     tile: torch.Tensor  # (n_items,) tile of each item
     local: torch.Tensor  # (n_items,) index of the item inside its tile
     value: torch.Tensor  # (n_items,) non-negative, < 2**bits
+    fill: int = 0  # value of the items nobody sets (e.g. padding lanes of a segment)
 
 
 def _pack(sections: list, n_tiles: int, device):
-    """Lay the sections of every tile out back to back; returns (tile_off int32, blob int32, words per tile)."""
+    """Lay the sections of every tile out back to back.
+
+    Returns (tile_off int64 [n_tiles+1], words int64 in [0, 2**32), words per tile)."""
     words = [_pad4((s.count * s.bits + 31) // 32) for s in sections]
     per_tile = sum(words)
     tile_off = torch.zeros(n_tiles + 1, dtype=torch.int64, device=device)
@@ -105,16 +161,51 @@ def _pack(sections: list, n_tiles: int, device):
         raise ValueError("tile plan too large for 32-bit word offsets")
     blob = torch.zeros(total, dtype=torch.int64, device=device)
     start = tile_off[:-1].clone()
+    tiles = torch.arange(n_tiles, device=device)
     for s, w in zip(sections, words):
+        per_word = 32 // s.bits
+        if s.fill:
+            # pre-fill the section's items (not the alignment padding behind them) with the pattern
+            n_items = s.count
+            item_tile = torch.repeat_interleave(tiles, n_items)
+            item_local = torch.arange(item_tile.numel(), device=device) - _excl_cumsum(n_items)[item_tile]
+            pos = start[item_tile] + torch.div(item_local, per_word, rounding_mode="floor")
+            blob.index_add_(0, pos, torch.full_like(pos, s.fill) << ((item_local % per_word) * s.bits))
         if s.value.numel():
-            per_word = 32 // s.bits
             if int(s.value.max().item()) >= 2**s.bits or int(s.value.min().item()) < 0:
                 raise ValueError(f"tile plan section {s.name}: value does not fit {s.bits} bits")
             pos = start[s.tile] + torch.div(s.local, per_word, rounding_mode="floor")
             shift = (s.local % per_word) * s.bits
-            blob.index_add_(0, pos, s.value.long() << shift)  # disjoint bit ranges: add == or
+            blob.index_add_(0, pos, (s.value.long() - s.fill) << shift)  # disjoint bit ranges: add == or
         start = start + w
-    return tile_off.to(torch.int32).contiguous(), _wrap_u32(blob), per_tile
+    return tile_off, blob, per_tile
+
+
+def _hash_tiles(tile_off: torch.Tensor, blob: torch.Tensor, n_tiles: int, seed: int) -> torch.Tensor:
+    """Two 61-bit positional hashes of every tile's words (no integer overflow: 16-bit halves times
+    31-bit multipliers, at most 2**14 words per tile)."""
+    device = blob.device
+    per_tile = tile_off[1:] - tile_off[:-1]
+    width = int(per_tile.max().item()) if n_tiles else 0
+    if width >= 2**14:
+        raise ValueError("tile blob too long to hash")
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    mult = torch.randint(1, 2**31 - 1, (4, max(width, 1)), generator=gen, dtype=torch.int64).to(device)
+    word_tile = torch.repeat_interleave(torch.arange(n_tiles, device=device), per_tile)
+    local = torch.arange(blob.numel(), device=device) - tile_off[word_tile]
+    lo, hi = (blob & 0xFFFF) + 1, (blob >> 16) + 1
+    out = torch.zeros((n_tiles, 2), dtype=torch.int64, device=device)
+    out[:, 0].index_add_(0, word_tile, lo * mult[0, local] + hi * mult[1, local])
+    out[:, 1].index_add_(0, word_tile, lo * mult[2, local] + hi * mult[3, local])
+    out[:, 0] += per_tile * 1000003
+    return out
+
+
+def _gather_ranges(blob: torch.Tensor, start: torch.Tensor, length: torch.Tensor) -> torch.Tensor:
+    """Concatenation of blob[start[k] : start[k] + length[k]] over k."""
+    which = torch.repeat_interleave(torch.arange(start.numel(), device=blob.device), length)
+    local = torch.arange(which.numel(), device=blob.device) - _excl_cumsum(length)[which]
+    return blob[start[which] + local]
 
 
 @dataclass
@@ -122,70 +213,64 @@ class TilePlan:
     """Device arrays of struct tfem_tile_plan plus bookkeeping."""
 
     n_tiles: int
-    e_off: torch.Tensor
-    e_blob: torch.Tensor
-    la_off: torch.Tensor
-    la_blob: torch.Tensor
-    lb_off: torch.Tensor
-    lb_blob: torch.Tensor
+    n_templates: int
+    tile_desc: torch.Tensor  # (n_tiles, 4) int32: instance word offset, instance words, template, 0
+    inst_blob: torch.Tensor  # int32
+    tpl_desc: torch.Tensor  # (n_templates, 4) int32: TB offset, TB words, TC offset, TC words
+    tpl_blob: torch.Tensor  # int32
+    default_order: torch.Tensor  # (n_tiles,) int32: all tiles, congruent ones adjacent
     max_vert: int
     max_elem: int
-    elem_stride: int  # row length of the shared local-matrix table; contribution codes index it directly
-    max_e_words: int
-    max_la_words: int
-    max_lb_words: int
     max_rows: int
-    max_out: int
+    max_segs: int
+    max_inst_words: int
+    max_tb_words: int
+    max_tc_words: int
     halo_factor: float  # tile elements / mesh elements (1.0 = every element integrated once)
-    index_bytes: int  # bytes of plan data the kernel reads per launch
-    consumer_threads: int = 0  # compute threads per CTA (128 / 256 / 384 / 512); 0 = library default
+    index_bytes: int  # bytes of plan data one launch reads (instances + each template once + descriptors)
+    lattice: tuple = None  # (W, bx, by) when the tiles are index-space blocks of a lattice-numbered mesh
+    consumer_threads: int = 0  # compute threads per CTA (256 / 384 / 512); 0 = library default
     tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
-    tile_list: torch.Tensor = None  # optional (n,) int32 subset of tiles to run (see `subset`)
+    tile_list: torch.Tensor = None  # optional (n,) int32 subset / order of tiles to run (see `subset`)
     reserve_ctas: int = 0  # CTA slots left free for kernels on other streams while this plan runs
     n_progress_tiles: int = 0  # the first tiles of `tile_list` report on `progress` when finished
     progress: torch.Tensor = None  # (1,) int32 device counter (see include/tfem_b200.h)
 
     def c_struct(self) -> "_lib.TilePlan":
         s = _lib.TilePlan()
-        s.n_tiles = self.n_tiles if self.tile_list is None else int(self.tile_list.numel())
-        s.tile_list = None if self.tile_list is None else self.tile_list.data_ptr()
-        s.e_off, s.e_blob = self.e_off.data_ptr(), self.e_blob.data_ptr()
-        s.la_off, s.la_blob = self.la_off.data_ptr(), self.la_blob.data_ptr()
-        s.lb_off, s.lb_blob = self.lb_off.data_ptr(), self.lb_blob.data_ptr()
-        s.max_vert, s.max_elem, s.max_e_words = self.max_vert, self.max_elem, self.max_e_words
-        s.max_la_words, s.max_lb_words = self.max_la_words, self.max_lb_words
-        s.elem_stride = self.elem_stride
+        order = self.default_order if self.tile_list is None else self.tile_list
+        s.n_tiles = int(order.numel())
+        s.tile_list = order.data_ptr()
+        s.tile_desc, s.inst_blob = self.tile_desc.data_ptr(), self.inst_blob.data_ptr()
+        s.tpl_desc, s.tpl_blob = self.tpl_desc.data_ptr(), self.tpl_blob.data_ptr()
+        s.max_vert, s.max_elem = self.max_vert, self.max_elem
+        s.max_inst_words, s.max_tb_words, s.max_tc_words = self.max_inst_words, self.max_tb_words, self.max_tc_words
         s.reserve_ctas = self.reserve_ctas
         s.n_progress_tiles = self.n_progress_tiles if self.progress is not None else 0
         s.progress = None if self.progress is None else self.progress.data_ptr()
         s.consumer_threads = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads))
+        self._keepalive = order  # the struct only holds raw pointers
         return s
 
     def subset(self, tile_ids: torch.Tensor, reserve_ctas: int = 0, n_progress_tiles: int = 0, progress: torch.Tensor = None) -> "TilePlan":
         """The same plan restricted to / reordered over some tiles (shares every array); used to
         assemble the tiles that hold multi-GPU interface rows first, with the first
         `n_progress_tiles` of them counted on `progress` so the exchange can start mid-launch."""
-        import dataclasses
-
         return dataclasses.replace(self, tile_list=tile_ids.to(torch.int32).contiguous(), reserve_ctas=reserve_ctas,
                                    n_progress_tiles=n_progress_tiles, progress=progress)
 
     @property
     def consumer_warps(self) -> int:
-        """Warps that report per finished tile on `progress` (library default: 256 consumer threads)."""
-        return (int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)) or 256) // 32
+        """Warps that report per finished tile on `progress`."""
+        return (int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)) or default_consumers(self.max_elem)) // 32
 
     def to(self, device) -> "TilePlan":
-        moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items()}
+        moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items() if not k.startswith("_")}
         return TilePlan(**moved)
 
     def sections(self, tile: int) -> dict:
-        """Decode one tile's blobs into named integer arrays (tests / debugging)."""
+        """Decode one tile's instance and template into named integer arrays (tests / debugging)."""
         import numpy as np
-
-        def words_of(off, blob):
-            o = off.cpu().numpy().astype("int64")
-            return blob[int(o[tile]) : int(o[tile + 1])].cpu().numpy().astype("int64") & 0xFFFFFFFF
 
         def unpack(words, pos, n, bits):
             n_words = (n * bits + 31) // 32
@@ -194,32 +279,37 @@ class TilePlan:
             vals = np.stack([(w >> (k * bits)) & (2**bits - 1) for k in range(per)], axis=1).reshape(-1)[:n]
             return vals, pos + ((n_words + 3) & ~3)
 
-        e = words_of(self.e_off, self.e_blob)
-        names = ("n_vert", "n_elem", "n_rows", "n_runs", "n_out", "n_chunks", "base_vertex", "n_heavy_contrib", "n_heavy")
-        out = {k: int(v) for k, v in zip(names, e[:HEADER_WORDS])}
-        pos = HEADER_WORDS
-        out["vert"], pos = unpack(e, pos, out["n_vert"], 32)
-        out["elem"], pos = unpack(e, pos, out["n_elem"], 32)
-        for off, blob, layout in (
-            (self.la_off, self.la_blob, (
-                ("run_start", out["n_runs"], 32),
-                ("run_meta", out["n_runs"], 32),
-                ("pair", out["n_out"], 32),
-                ("heavy_seg", out["n_heavy"] + 1, 16),
-                ("heavy_contrib", out["n_heavy_contrib"], 16),
-                ("heavy_pos", out["n_heavy"], 32),
-            )),
-            (self.lb_off, self.lb_blob, (
-                ("row_id", out["n_rows"], 32),
-                ("row_chunk", 8 * out["n_chunks"], 16),
-                ("row_diag", out["n_rows"], 32),
-            )),
-        ):
-            lw = words_of(off, blob)
-            pos = 0
-            for name, n, bits in layout:
-                out[name], pos = unpack(lw, pos, n, bits)
+        inst_off, inst_words, tpl, _ = self.tile_desc[tile].tolist()
+        inst = self.inst_blob[inst_off : inst_off + inst_words].cpu().numpy().astype("int64") & 0xFFFFFFFF
+        tb_off, tb_words, tc_off, tc_words = self.tpl_desc[tpl].tolist()
+        tb = self.tpl_blob[tb_off : tb_off + tb_words].cpu().numpy().astype("int64") & 0xFFFFFFFF
+        tc = self.tpl_blob[tc_off : tc_off + tc_words].cpu().numpy().astype("int64") & 0xFFFFFFFF
+        out = {"template": tpl, "inst_offset": inst_off, "tb_offset": tb_off, "tc_offset": tc_off}
+        names = ("n_vert", "n_elem", "n_rows", "n_segs", "n_chunks", "n_heavy", "n_heavy_contrib")
+        out.update({k: int(v) for k, v in zip(names, tb[:TB_HEADER_WORDS])})
+        out["inst_header"] = inst[:INST_HEADER_WORDS].tolist()
+        out["base_vertex"] = int(inst[3])
+        pos = INST_HEADER_WORDS
+        out["vert"], pos = unpack(inst, pos, out["n_vert"], 32)
+        out["seg_start"], pos = unpack(inst, pos, out["n_segs"], 32)
+        out["row_id"], pos = unpack(inst, pos, out["n_rows"], 32)
+        assert pos == inst_words
+        out["elem"], pos = unpack(tb, TB_HEADER_WORDS, out["n_elem"], 32)
+        assert pos == tb_words
+        pos = 0
+        out["pair"], pos = unpack(tc, pos, SEG * out["n_segs"], 32)
+        out["row_chunk"], pos = unpack(tc, pos, 8 * out["n_chunks"], 16)
+        out["row_diag"], pos = unpack(tc, pos, out["n_rows"], 16)
+        out["heavy_seg"], pos = unpack(tc, pos, out["n_heavy"] + 1, 16)
+        out["heavy_contrib"], pos = unpack(tc, pos, out["n_heavy_contrib"], 16)
+        out["heavy_pos"], pos = unpack(tc, pos, out["n_heavy"], 16)
+        assert pos == tc_words
         return out
+
+
+def default_consumers(max_elem: int) -> int:
+    """Compute threads per CTA the library picks for a plan (mirrors assemble_tiled.cu)."""
+    return 384
 
 
 def build_tile_plan(
@@ -227,8 +317,9 @@ def build_tile_plan(
     dof_conn: torch.Tensor,
     pattern: CsrPattern,
     row_points: torch.Tensor | None = None,
-    rows_per_tile: int = 192,
-    ordering: str = "block",
+    rows_per_tile: int = 336,
+    ordering: str = "auto",
+    tile_shape: tuple | None = None,
 ) -> TilePlan:
     """Partition CSR rows into tiles and precompute everything the fused kernel gathers.
 
@@ -236,6 +327,9 @@ def build_tile_plan(
     dof_conn  (N,3): global DOF (CSR row/col) of each element vertex.
     row_points (n_dof,2+): a position per DOF, only used to cluster rows spatially; with
     None, tiles are runs of consecutive DOF ids.
+    ordering: "auto" = index-space blocks when the numbering is a lattice (`detect_lattice`), else
+    "block" (square spatial blocks); "morton" / "natural" = balanced chunks along a Z-order curve /
+    of consecutive ids.  `tile_shape` = (bx, by) overrides the lattice block extent.
     """
     device = dof_conn.device
     gconn = geom_conn.reshape(-1, 3).long()
@@ -254,7 +348,21 @@ def build_tile_plan(
     active_rows = torch.nonzero(active, as_tuple=True)[0]
     n_active = int(active_rows.numel())
     tile_of_active = None
-    if row_points is not None and ordering == "block" and n_active:
+    lattice = None
+    if ordering in ("auto", "lattice") and n_active:
+        width = detect_lattice(pattern)
+        if width:
+            bx, by = tile_shape if tile_shape is not None else lattice_shape(rows_per_tile)
+            nbx = (width + bx - 1) // bx  # a leftover column / row of blocks is simply narrower
+            li, lj = active_rows % width, torch.div(active_rows, width, rounding_mode="floor")
+            ti = torch.div(li, bx, rounding_mode="floor")
+            tj = torch.div(lj, by, rounding_mode="floor")
+            used, tile_of_active = torch.unique(tj * nbx + ti, return_inverse=True)
+            n_tiles = int(used.numel())
+            lattice = (width, bx, by)
+        elif ordering == "lattice":
+            raise ValueError("the DOF numbering is not a lattice: use ordering='block'")
+    if tile_of_active is None and row_points is not None and ordering in ("auto", "block") and n_active:
         tile_of_active, n_tiles, largest = block_tiles(row_points[active_rows], rows_per_tile)
         if largest > 2 * rows_per_tile:  # strongly graded mesh: fall back to balanced Z-order chunks
             tile_of_active = None
@@ -288,49 +396,49 @@ def build_tile_plan(
     n_v = vert_ptr[1:] - vert_ptr[:-1]
     local_v = torch.searchsorted(vert_keys, vkeys_all.reshape(-1)).reshape(-1, 3) - vert_ptr[pair_tile][:, None]
     max_vert, max_elem = int(n_v.max().item()), int(n_e.max().item())
-    if max_vert > 1024 or max_elem > 4096:
-        raise ValueError(f"tile too large (vertices {max_vert} > 1024 or elements {max_elem} > 4096): lower rows_per_tile")
+    if max_vert > MAX_VERT or max_elem > MAX_ELEM:
+        raise ValueError(f"tile too large (vertices {max_vert} > {MAX_VERT} or elements {max_elem} > {MAX_ELEM}): lower rows_per_tile")
     tile_elem = local_v[:, 0] | (local_v[:, 1] << 10) | (local_v[:, 2] << 20)
-    middle = (vert_ptr[:-1] + torch.div(n_v, 2, rounding_mode="floor")).clamp_max(max(tile_vert.numel() - 1, 0))
-    base_vertex = torch.where(n_v > 0, tile_vert[middle] if tile_vert.numel() else torch.zeros_like(n_v), torch.zeros_like(n_v))
+    base_vertex = torch.div(n_v, 2, rounding_mode="floor")  # tile-local index of a vertex near the middle of the id range
 
-    # 4. rows of each tile, ascending row id; runs of consecutive rows = contiguous CSR ranges
+    # 4. rows of each tile, ascending row id; runs of consecutive rows = contiguous CSR ranges,
+    #    cut into segments of at most 32 entries (one warp pass each)
     row_sorted = torch.argsort(tile_of_row * n_dof + arange(n_dof))
     row_tile = tile_of_row[row_sorted]
     row_ptr = _ptr(row_tile, n_tiles)
     n_r = row_ptr[1:] - row_ptr[:-1]
     row_len = crow[row_sorted + 1] - crow[row_sorted]
-    row_out = _excl_cumsum(row_len)  # image offset over all tile-ordered rows
-    tile_out0 = row_out[row_ptr[:-1].clamp_max(max(n_dof - 1, 0))]  # image offset of each tile's first row
-    n_out = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, row_tile, row_len)
     new_run = torch.ones(n_dof, dtype=torch.bool, device=device)
     if n_dof > 1:
         new_run[1:] = (row_tile[1:] != row_tile[:-1]) | (row_sorted[1:] != row_sorted[:-1] + 1)
     run_first = torch.nonzero(new_run, as_tuple=True)[0]
     run_last = torch.cat([run_first[1:], torch.tensor([n_dof], device=device)]) - 1
+    run_of_row = torch.cumsum(new_run.long(), 0) - 1
     whole_start = crow[row_sorted[run_first]]
     whole_len = crow[row_sorted[run_last] + 1] - whole_start
-    whole_base = row_out[run_first] - tile_out0[row_tile[run_first]]
-    # ... cut into segments of at most 32 entries: one warp, one lane per entry, no inner loop
-    SEG = 32
     pieces = torch.div(whole_len + SEG - 1, SEG, rounding_mode="floor")
+    piece0 = _excl_cumsum(pieces)  # global index of each run's first segment
     piece_run = torch.repeat_interleave(arange(whole_len.numel()), pieces)
-    piece_k = arange(piece_run.numel()) - _excl_cumsum(pieces)[piece_run]
-    run_tile = row_tile[run_first][piece_run]
-    run_ptr = _ptr(run_tile, n_tiles)
-    n_u = run_ptr[1:] - run_ptr[:-1]
-    run_start = whole_start[piece_run] + SEG * piece_k
-    run_len = (whole_len[piece_run] - SEG * piece_k).clamp_max(SEG)
-    run_base = whole_base[piece_run] + SEG * piece_k
-    if int(n_out.max().item()) > 65535 or int(n_u.max().item()) > 65535:
-        raise ValueError("tile image too large (entries or segments > 65535): lower rows_per_tile")
+    piece_k = arange(piece_run.numel()) - piece0[piece_run]
+    seg_tile = row_tile[run_first][piece_run]
+    seg_ptr = _ptr(seg_tile, n_tiles)
+    n_s = seg_ptr[1:] - seg_ptr[:-1]
+    seg_start = whole_start[piece_run] + SEG * piece_k
+    if int(n_s.max().item()) > MAX_SEGS:
+        raise ValueError("tile has too many entry segments: lower rows_per_tile")
 
-    # 5. every CSR entry of a tile with its contributions (element ascending = reference order)
+    # 5. every CSR entry of a tile (tile-ordered rows, columns ascending) with its (segment, lane)
+    #    and its contributions (element ascending = reference order)
     nnz = pattern.nnz
-    ent_row = torch.repeat_interleave(arange(n_dof), row_len)  # tile-ordered row index of each image slot
-    ent_global = crow[row_sorted[ent_row]] + (arange(nnz) - row_out[ent_row])
+    row_out = _excl_cumsum(row_len)
+    ent_row = torch.repeat_interleave(arange(n_dof), row_len)  # tile-ordered row index of each entry
+    ent_k = arange(nnz) - row_out[ent_row]
+    ent_global = crow[row_sorted[ent_row]] + ent_k
     ent_tile = row_tile[ent_row]
-    ent_local = arange(nnz) - tile_out0[ent_tile]
+    ent_run = run_of_row[ent_row]
+    ent_off = ent_global - whole_start[ent_run]
+    ent_seg = piece0[ent_run] + torch.div(ent_off, SEG, rounding_mode="floor") - seg_ptr[ent_tile]  # tile-local segment
+    ent_code = ent_seg * SEG + ent_off % SEG
     seg = pattern.seg.long()
     ent_cnt = seg[ent_global + 1] - seg[ent_global]
     ent_coff = _excl_cumsum(ent_cnt)
@@ -343,14 +451,8 @@ def build_tile_plan(
     c_j = coo - 9 * c_e - 3 * c_i
     slot = torch.where(c_i == c_j, c_i, 3 + (c_i + c_j == 3).long() + 2 * (c_i + c_j == 2).long())  # K00 K11 K22 K01 K12 K20
     c_tile = ent_tile[c_ent]
-    # sloc is [9][elem_stride]; codes `slot*elem_stride + element` index it directly.  The last
-    # column (element elem_stride-1) is never written by the integration phase and holds zeros:
-    # `zero_code` pads every fixed-length contribution list.
-    elem_stride = (max_elem + 1 + 31) & ~31
-    zero_code = elem_stride - 1
-    if 9 * elem_stride > 65535:
-        raise ValueError("tile has too many elements for 16-bit local-matrix indices: lower rows_per_tile")
-    c_code = (torch.searchsorted(pair_keys, c_tile * n_el + c_e) - elem_ptr[c_tile]) + slot * elem_stride
+    # the CTA's local table is [1 + tile elements][9]; row 0 stays zero, so code 0 = "no contribution"
+    c_code = (torch.searchsorted(pair_keys, c_tile * n_el + c_e) - elem_ptr[c_tile] + 1) * N_SLOTS + slot
 
     # 6. load-vector contributions per owned row
     lseg = pattern.lin_seg.long()
@@ -363,23 +465,22 @@ def build_tile_plan(
     lc_e = torch.div(lc_flat, 3, rounding_mode="floor")
     lc_k = lc_flat - 3 * lc_e
     lc_tile = row_tile[lc_row]
-    lc_code = (torch.searchsorted(pair_keys, lc_tile * n_el + lc_e) - elem_ptr[lc_tile]) + lc_k * elem_stride
+    lc_code = (torch.searchsorted(pair_keys, lc_tile * n_el + lc_e) - elem_ptr[lc_tile] + 1) * N_SLOTS + lc_k
 
-    # 6b. who sums which entry.  One thread per entry handles entries with <= 2 contributions
-    #     (every off-diagonal entry of a manifold mesh) from ONE packed word, without a loop; the
-    #     diagonal of a row is summed by the row's thread together with its load entry (same element
-    #     list); anything else with > 2 contributions (non-manifold edges, degenerate elements)
-    #     goes to a short "heavy" list handled by a generic loop.
+    # 6b. who sums which entry.  One lane per entry handles entries with <= 2 contributions (every
+    #     off-diagonal entry of a manifold mesh) from ONE packed word, without a loop; the diagonal of
+    #     a row is summed by the row's thread together with its load entry (same element list);
+    #     anything else with > 2 contributions (non-manifold edges, degenerate elements) goes to a
+    #     short "heavy" list handled by a generic loop.
     ent_is_diag = pattern.col.long()[ent_global] == row_sorted[ent_row]
     off_slot = torch.zeros(nnz, dtype=torch.int64, device=device).index_add_(0, c_ent, (slot >= 3).long())
     diag_fast = ent_is_diag & (ent_cnt > 2) & (off_slot == 0) & (ent_cnt == lrow_cnt[ent_row])
-    row_diag = torch.full((n_dof,), 0xFFFFFFFF, dtype=torch.int64, device=device)  # CSR position or none
-    row_diag[ent_row[diag_fast]] = ent_global[diag_fast]
+    row_diag = torch.full((n_dof,), 0xFFFF, dtype=torch.int64, device=device)
+    row_diag[ent_row[diag_fast]] = ent_code[diag_fast]
     heavy = (ent_cnt > 2) & ~diag_fast
     heavy_tile = ent_tile[heavy]
     n_h = torch.bincount(heavy_tile, minlength=n_tiles)
     heavy_local = arange(heavy_tile.numel()) - _excl_cumsum(n_h)[heavy_tile]
-    # contributions of the heavy entries, with per-tile offsets (n_h + 1 values per tile)
     heavy_ids = torch.nonzero(heavy, as_tuple=True)[0]
     heavy_cnt = ent_cnt[heavy_ids]
     n_hc = torch.zeros(n_tiles, dtype=torch.int64, device=device).index_add_(0, heavy_tile, heavy_cnt)
@@ -396,20 +497,19 @@ def build_tile_plan(
     heavy_coff_ext = torch.cat([heavy_coff, torch.tensor([total_hc], device=device)])
     hseg_value = heavy_coff_ext[_excl_cumsum(n_h)[hseg_tile] + hseg_local] - tile_hc0[hseg_tile]
 
-    # 6c. the packed pair of every entry: lo 16 bits = first contribution, hi 16 = second (zero_code
-    #     when absent); 0xFFFFFFFF = "not mine" (diagonal done by the row thread, or heavy)
-    first = torch.full((nnz,), zero_code, dtype=torch.int64, device=device)
-    second = torch.full((nnz,), zero_code, dtype=torch.int64, device=device)
+    # 6c. the packed pair of every entry: lo 16 bits = first contribution, hi 16 = second (0 when
+    #     absent); 0xFFFFFFFF = "not mine" (diagonal done by the row thread, heavy, or a padding lane)
+    first = torch.zeros(nnz, dtype=torch.int64, device=device)
+    second = torch.zeros(nnz, dtype=torch.int64, device=device)
     first[c_ent[c_within == 0]] = c_code[c_within == 0]
     second[c_ent[c_within == 1]] = c_code[c_within == 1]
     pair = first | (second << 16)
     pair[ent_cnt > 2] = 0xFFFFFFFF
 
-    # 6d. per-row chunks of 8 x u16: 7 contribution codes (k*elem_stride + element; zero_code pads)
-    #     and the tile-local index of the row's next chunk (0 = none).  Chunk j < n_rows is the first
-    #     chunk of row j; rows with more than 7 elements continue in chunks appended after n_rows.
-    PER = 7
-    row_chunks = torch.div(lrow_cnt + PER - 1, PER, rounding_mode="floor").clamp_min(1)
+    # 6d. per-row chunks of 8 x u16: 7 contribution codes ((element+1)*9 + local vertex k; 0 pads) and the
+    #     tile-local index of the row's next chunk (0 = none).  Chunk j < n_rows is the first chunk of
+    #     row j; rows with more than 7 elements continue in chunks appended after n_rows.
+    row_chunks = torch.div(lrow_cnt + PER_CHUNK - 1, PER_CHUNK, rounding_mode="floor").clamp_min(1)
     row_extra = row_chunks - 1
     extra_off = _excl_cumsum(row_extra)
     extra_in_tile = extra_off - extra_off[row_ptr[:-1].clamp_max(max(n_dof - 1, 0))][row_tile]
@@ -419,13 +519,11 @@ def build_tile_plan(
         raise ValueError("tile has more than 65535 row chunks: lower rows_per_tile")
     chunk0 = _excl_cumsum(n_ch)
     total_ch = int(n_ch.sum().item())
-    chunks = torch.full((total_ch, 8), zero_code, dtype=torch.int64, device=device)
-    chunks[:, 7] = 0
+    chunks = torch.zeros((total_ch, 8), dtype=torch.int64, device=device)
     row_local = arange(n_dof) - row_ptr[row_tile]
-    lc_q = torch.div(lc_within, PER, rounding_mode="floor")
+    lc_q = torch.div(lc_within, PER_CHUNK, rounding_mode="floor")
     lc_chunk_local = torch.where(lc_q == 0, row_local[lc_row], n_r[lc_tile] + extra_in_tile[lc_row] + lc_q - 1)
-    chunks[chunk0[lc_tile] + lc_chunk_local, lc_within - PER * lc_q] = lc_code
-    # links: chunk q of a row -> chunk q+1
+    chunks[chunk0[lc_tile] + lc_chunk_local, lc_within - PER_CHUNK * lc_q] = lc_code
     link_row = torch.repeat_interleave(arange(n_dof), row_extra)
     link_q = arange(link_row.numel()) - extra_off[link_row]  # 0-based: link from chunk q to q+1
     link_tile = row_tile[link_row]
@@ -435,49 +533,76 @@ def build_tile_plan(
     chunk_tile = torch.repeat_interleave(tiles, n_ch * 8)
     chunk_local = arange(total_ch * 8) - (chunk0 * 8)[chunk_tile]
 
-    # 7. pack
-    header = torch.stack([n_v, n_e, n_r, n_u, n_out, n_ch, base_vertex, n_hc, n_h, n_h * 0, n_h * 0, n_h * 0], dim=1).reshape(-1)
-    hdr_tile = torch.repeat_interleave(tiles, HEADER_WORDS)
-    hdr_local = arange(hdr_tile.numel()) % HEADER_WORDS
-    e_sections = [
-        _Section("header", 32, torch.full_like(n_v, HEADER_WORDS), hdr_tile, hdr_local, header),
+    # 7. pack: instances, and the two template blobs of every tile
+    def header(columns, words):
+        stacked = torch.stack(columns + [torch.zeros_like(n_v)] * (words - len(columns)), dim=1).reshape(-1)
+        tile = torch.repeat_interleave(tiles, words)
+        return _Section("header", 32, torch.full_like(n_v, words), tile, arange(tile.numel()) % words, stacked)
+
+    seg_local = arange(seg_tile.numel()) - seg_ptr[seg_tile]
+    inst_sections = [
+        header([n_v, n_s, n_r, base_vertex], INST_HEADER_WORDS),
         _Section("vert", 32, n_v, vert_tile, arange(vert_tile.numel()) - vert_ptr[vert_tile], tile_vert),
+        _Section("seg_start", 32, n_s, seg_tile, seg_local, seg_start),
+        _Section("row_id", 32, n_r, row_tile, row_local, row_sorted),
+    ]
+    tb_sections = [
+        header([n_v, n_e, n_r, n_s, n_ch, n_h, n_hc], TB_HEADER_WORDS),
         _Section("elem", 32, n_e, pair_tile, arange(pair_tile.numel()) - elem_ptr[pair_tile], tile_elem),
     ]
-    run_local = arange(run_tile.numel()) - run_ptr[run_tile]
-    la_sections = [
-        _Section("run_start", 32, n_u, run_tile, run_local, run_start),
-        _Section("run_meta", 32, n_u, run_tile, run_local, run_base | (run_len << 16)),
-        _Section("pair", 32, n_out, ent_tile, ent_local, pair),
+    tc_sections = [
+        _Section("pair", 32, n_s * SEG, ent_tile, ent_code, pair, fill=0xFFFFFFFF),
+        _Section("row_chunk", 16, n_ch * 8, chunk_tile, chunk_local, chunks.reshape(-1)),
+        _Section("row_diag", 16, n_r, row_tile, row_local, row_diag),
         _Section("heavy_seg", 16, n_h + 1, hseg_tile, hseg_local, hseg_value),
         _Section("heavy_contrib", 16, n_hc, hc_tile, arange(total_hc) - tile_hc0[hc_tile], hc_code),
-        _Section("heavy_pos", 32, n_h, heavy_tile, heavy_local, ent_global[heavy]),
+        _Section("heavy_pos", 16, n_h, heavy_tile, heavy_local, ent_code[heavy]),
     ]
-    lb_sections = [
-        _Section("row_id", 32, n_r, row_tile, row_local, row_sorted),
-        _Section("row_chunk", 16, n_ch * 8, chunk_tile, chunk_local, chunks.reshape(-1)),
-        _Section("row_diag", 32, n_r, row_tile, row_local, row_diag),
-    ]
-    e_off, e_blob, e_words = _pack(e_sections, n_tiles, device)
-    la_off, la_blob, la_words = _pack(la_sections, n_tiles, device)
-    lb_off, lb_blob, lb_words = _pack(lb_sections, n_tiles, device)
+    inst_off, inst_blob, inst_words = _pack(inst_sections, n_tiles, device)
+    tb_off, tb_blob, tb_words = _pack(tb_sections, n_tiles, device)
+    tc_off, tc_blob, tc_words = _pack(tc_sections, n_tiles, device)
+
+    # 8. congruent tiles share one template
+    signature = torch.cat([_hash_tiles(tb_off, tb_blob, n_tiles, 1), _hash_tiles(tc_off, tc_blob, n_tiles, 2)], dim=1)
+    _, template_of, counts = torch.unique(signature, dim=0, return_inverse=True, return_counts=True)
+    n_templates = int(counts.numel())
+    # representative = first tile of each template; templates numbered by decreasing population
+    by_count = torch.argsort(counts, descending=True, stable=True)
+    rank = torch.empty_like(by_count)
+    rank[by_count] = arange(n_templates)
+    template_of = rank[template_of]
+    rep = torch.full((n_templates,), n_tiles, dtype=torch.int64, device=device).scatter_reduce_(0, template_of, tiles, reduce="amin")
+    rep_tb_words, rep_tc_words = tb_words[rep], tc_words[rep]
+    tpl_words = torch.stack([rep_tb_words, rep_tc_words], dim=1).reshape(-1)
+    tpl_offsets = _excl_cumsum(tpl_words).reshape(-1, 2)
+    tpl_blob = torch.empty(int(tpl_words.sum().item()), dtype=torch.int64, device=device)
+    tb_part = _gather_ranges(tb_blob, tb_off[rep], rep_tb_words)
+    tc_part = _gather_ranges(tc_blob, tc_off[rep], rep_tc_words)
+    tb_dst = torch.repeat_interleave(tpl_offsets[:, 0], rep_tb_words) + (arange(tb_part.numel()) - torch.repeat_interleave(_excl_cumsum(rep_tb_words), rep_tb_words))
+    tc_dst = torch.repeat_interleave(tpl_offsets[:, 1], rep_tc_words) + (arange(tc_part.numel()) - torch.repeat_interleave(_excl_cumsum(rep_tc_words), rep_tc_words))
+    tpl_blob[tb_dst] = tb_part
+    tpl_blob[tc_dst] = tc_part
+    tpl_desc = torch.stack([tpl_offsets[:, 0], rep_tb_words, tpl_offsets[:, 1], rep_tc_words], dim=1).to(torch.int32).contiguous()
+    tile_desc = torch.stack([inst_off[:-1], inst_words, template_of, torch.zeros_like(template_of)], dim=1).to(torch.int32).contiguous()
+    default_order = torch.argsort(template_of * n_tiles + tiles).to(torch.int32).contiguous()
+
     return TilePlan(
         n_tiles=n_tiles,
-        e_off=e_off,
-        e_blob=e_blob,
-        la_off=la_off,
-        la_blob=la_blob,
-        lb_off=lb_off,
-        lb_blob=lb_blob,
+        n_templates=n_templates,
+        tile_desc=tile_desc,
+        inst_blob=_wrap_u32(inst_blob),
+        tpl_desc=tpl_desc,
+        tpl_blob=_wrap_u32(tpl_blob),
+        default_order=default_order,
         max_vert=max_vert,
         max_elem=max_elem,
-        elem_stride=elem_stride,
-        max_e_words=int(e_words.max().item()),
-        max_la_words=int(la_words.max().item()),
-        max_lb_words=int(lb_words.max().item()),
         max_rows=int(n_r.max().item()),
-        max_out=int(n_out.max().item()),
+        max_segs=int(n_s.max().item()),
+        max_inst_words=int(inst_words.max().item()),
+        max_tb_words=int(tb_words.max().item()),
+        max_tc_words=int(tc_words.max().item()),
         halo_factor=float(pair_keys.shape[0]) / max(n_el, 1),
-        index_bytes=4 * (e_blob.numel() + la_blob.numel() + lb_blob.numel() + e_off.numel() + la_off.numel() + lb_off.numel()),
+        index_bytes=4 * (inst_blob.numel() + tpl_blob.numel() + tile_desc.numel() + tpl_desc.numel() + default_order.numel()),
+        lattice=lattice,
         tile_of_row=tile_of_row,
     )
