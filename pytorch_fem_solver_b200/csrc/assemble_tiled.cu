@@ -633,6 +633,12 @@ int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>& q
 template <typename T, int CONSUMERS, int ORDER>
 int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>& quad, cudaStream_t s) {
   const int kind = args.load ? args.src.kind : TFEM_SRC_NONE;
+#ifdef TFEM_FAST_BUILD  // experiment builds: only the headline instantiation (fp64, 4-point rule, K+M and sin-sin load)
+  if constexpr (sizeof(T) == 8 && ORDER == 3) {
+    if (args.csr_val && kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, quad, s);
+  }
+  return TFEM_ERR_UNSUPPORTED;
+#else
   if (args.csr_val) {
     if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, quad, s);
     if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true>(hp, args, quad, s);
@@ -641,6 +647,7 @@ int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>&
   if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, false>(hp, args, quad, s);
   if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, false>(hp, args, quad, s);
   return TFEM_ERR_BAD_ARG;
+#endif
 }
 
 template <typename T>
