@@ -87,16 +87,21 @@ typedef struct tfem_bilinear {
  *   template, part TC (reduction phase)
  *     pair[n_segs][32]     u32  one word per lane of each segment: lane l of segment s owns
  *                               csr_val[seg_start[s] + l].  lo 16 bits = first, hi 16 bits = second
- *                               contribution, each a code (tile element + 1) * 9 + slot (slot 0..5 =
- *                               K00 K11 K22 K01 K12 K20, 6..8 = load), i.e. a direct index into the
- *                               CTA's local table [1 + n_elem][9] whose row 0 holds zeros (code 0 =
- *                               "no contribution"), in increasing element id (the summation order of
- *                               the reference's index_put_/coalesce); 0xFFFFFFFF = lane without an
- *                               entry, or entry summed elsewhere (row_diag or the heavy list)
- *     row_chunk[n_chunks][8] u16  chunk j < n_rows belongs to owned row j: 7 codes
- *                               (tile element + 1) * 9 + k (k = local vertex) of the elements around
- *                               the row's vertex, padded with 0; the code indexes the row's diagonal
- *                               term, its load term sits 6 slots further; the 8th value is the index of
+ *                               contribution, each a CODE = byte offset (fp64) of a local value in the
+ *                               CTA's local table, in increasing element id (the summation order of the
+ *                               reference's index_put_/coalesce); code 0 = "no contribution" (a zero);
+ *                               0xFFFFFFFF = lane without an entry, or entry summed elsewhere (row_diag or
+ *                               the heavy list).  The table has R = max_elem + 2 rows (row 0 = zeros,
+ *                               row 1 + p = the tile element at position p of elem[], last row = scratch):
+ *                                 48 * row + 16 * k      diagonal term of local vertex k   (K00 K11 K22)
+ *                                 48 * row + 16 * k + 8  load term of local vertex k
+ *                                 od_base[m] + 8 * row   off-diagonal term m = 0, 1, 2     (K01 K12 K20)
+ *                               (elem[] lists a tile's elements in ascending id, or even positions first
+ *                               and odd positions second: whichever gives fewer shared-memory bank
+ *                               conflicts; od_base likewise -- see tileplan._choose_layout)
+ *     row_chunk[n_chunks][8] u16  chunk j < n_rows belongs to owned row j: 7 codes of the diagonal terms
+ *                               of the elements around the row's vertex (ascending element id), padded
+ *                               with 0; the load term sits 8 bytes further; the 8th value is the index of
  *                               the row's next chunk (rows with more than 7 elements), 0 = none
  *     row_diag[n_rows]     u16  entry code (segment * 32 + lane) of the row's diagonal when the row's
  *                               thread sums it (same element list as the load entry), else 0xFFFF
@@ -117,6 +122,8 @@ typedef struct tfem_tile_plan {
   const int32_t* tpl_desc;   /* [templates][4]: TB word offset, TB words, TC word offset, TC words */
   const int32_t* tpl_blob;
   int32_t max_vert, max_elem, max_inst_words, max_tb_words, max_tc_words; /* per-tile maxima (shared-memory sizing) */
+  int32_t table_bytes;      /* size of the CTA's local table in fp64 bytes (the fp32 kernels use half) */
+  int32_t od_base[3];       /* byte offsets of the off-diagonal arrays K01, K12, K20 inside the table (see below) */
   int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = library default (384) */
   int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
                                (interface pack / signal / add) can run beside it; 0 = use every slot */

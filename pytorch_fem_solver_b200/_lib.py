@@ -55,6 +55,8 @@ class TilePlan(Structure):
         ("max_inst_words", c_int32),
         ("max_tb_words", c_int32),
         ("max_tc_words", c_int32),
+        ("table_bytes", c_int32),
+        ("od_base", c_int32 * 3),
         ("consumer_threads", c_int32),
         ("reserve_ctas", c_int32),
         ("n_progress_tiles", c_int32),

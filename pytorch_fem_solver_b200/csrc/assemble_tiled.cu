@@ -119,9 +119,45 @@ __device__ __forceinline__ void consumer_sync() {
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 constexpr int kInstHeader = 4;
 constexpr int kTbHeader = 8;
-constexpr int kInstStages = 3;   // instance blobs in flight
-constexpr int kSlots = 9;        // K00 K11 K22 K01 K12 K20 b0 b1 b2
-constexpr int kSmemHeader = 384; // mbarriers, two stage records, two base-point records
+constexpr int kInstStages = 3;    // instance blobs in flight
+constexpr int kDlSlots = 6;       // one "dl" table row per tile element: d0 b0 d1 b1 d2 b2 (include/tfem_b200.h)
+constexpr int kSmemHeader = 384;  // mbarriers, two stage records, two base-point records
+
+// ---- shared-memory accesses by 32-bit address (no generic-pointer arithmetic in the hot loops) --
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void lds_2(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds_2(uint32_t a, float& x, float& y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds_1(uint32_t a, double& x) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a)); }
+__device__ __forceinline__ void lds_1(uint32_t a, float& x) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a)); }
+__device__ __forceinline__ void sts_2(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void sts_2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void sts_1(uint32_t a, double x) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory"); }
+__device__ __forceinline__ void sts_1(uint32_t a, float x) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory"); }
+// plan codes are byte offsets into a table of fp64 slots; the fp32 table is half as wide
+template <typename T>
+__device__ __forceinline__ uint32_t code_offset(uint32_t code) { return sizeof(T) == 8 ? code : code >> 1; }
 
 template <int ORDER> struct NQ;
 template <> struct NQ<1> { static constexpr int value = 1; };
@@ -132,8 +168,10 @@ template <> struct NQ<4> { static constexpr int value = 6; };
 __device__ __forceinline__ void sincos_full(double x, double& s, double& c) { sincos(x, &s, &c); }
 __device__ __forceinline__ void sincos_full(float x, float& s, float& c) { sincosf(x, &s, &c); }
 
-// Magnitude keys: order-preserving integer images of |v| (the high word for doubles), so that the
-// largest of several magnitudes and a threshold test cost integer max / one warp reduction.
+// Magnitude keys: order-preserving integer images of |v| (the high word for doubles), so that
+// threshold tests cost integer max / compare instead of fp64 instructions.
+__device__ __forceinline__ int hi_word(double v) { return __double2hiint(v); }
+__device__ __forceinline__ int hi_word(float v) { return __float_as_int(v); }
 __device__ __forceinline__ int mag_key(double v) { return __double2hiint(v) & 0x7fffffff; }
 __device__ __forceinline__ int mag_key(float v) { return __float_as_int(v) & 0x7fffffff; }
 inline int host_mag_key(double v, double) {
@@ -161,60 +199,94 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 __device__ __forceinline__ float fast_rcp(float d) { return __frcp_rn(d); }
 
+// Every floating-point constant of the hot loop, passed as a kernel parameter: operands then come
+// from the constant bank (one load feeds two constants) instead of two immediate moves per use.
+template <typename T>
+struct TiledConst {
+  T w1_3, w2_3;                 // source frequencies / 3 (phase of the centroid)
+  T s3, s5, s7, s9;             // sin(t) = t + t^3 (s3 + t^2 (s5 + t^2 (s7 + t^2 s9)))
+  T c2, c4, c6, c8, c10;        // cos(t) = 1 + t^2 (c2 + t^2 (c4 + ...))
+  T f[9];                       // signed inverse factorials of sin(a + t) = sum_d f[d] t^d {sin a | cos a}
+  T kcw, md, mo;                // alpha * sum_q w_q ; beta * reference mass (diagonal, off-diagonal)
+  T c1[kMaxQ], c2q[kMaxQ];      // barycentric offsets of the quadrature points from the centroid
+  T wl0[kMaxQ], wl1[kMaxQ], wl2[kMaxQ];  // w_q * l_i(q)
+  T m0, m1, m2;                 // sum_q w_q l_i(q)  (constant source)
+};
+
+template <typename T>
+TiledConst<T> make_tiled_const(int order, const QuadT<T>& quad, T alpha, T beta, const SourceT<T>& src) {
+  TiledConst<T> c{};
+  c.w1_3 = T(double(src.p1) / 3.0);
+  c.w2_3 = T(double(src.p2) / 3.0);
+  c.s3 = T(-1.0 / 6.0); c.s5 = T(1.0 / 120.0); c.s7 = T(-1.0 / 5040.0); c.s9 = T(1.0 / 362880.0);
+  c.c2 = T(-0.5); c.c4 = T(1.0 / 24.0); c.c6 = T(-1.0 / 720.0); c.c8 = T(1.0 / 40320.0); c.c10 = T(-1.0 / 3628800.0);
+  const double inv_fact[9] = {1.0, 1.0, -1.0 / 2.0, -1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, -1.0 / 720.0, -1.0 / 5040.0, 1.0 / 40320.0};
+  for (int d = 0; d < 9; ++d) c.f[d] = T(inv_fact[d]);
+  c.kcw = alpha * quad.wsum;
+  c.md = beta * quad.mref[0];
+  c.mo = beta * quad.mref[1];
+  const TriTable tt = tri_table(order);
+  double m0 = 0, m1 = 0, m2 = 0;
+  for (int q = 0; q < tt.n_q; ++q) {
+    const double l1 = tt.xi[q], l2 = tt.eta[q], l0 = 1.0 - l1 - l2, w = 0.5 * tt.w[q];
+    c.c1[q] = T(l1 - 1.0 / 3.0);
+    c.c2q[q] = T(l2 - 1.0 / 3.0);
+    c.wl0[q] = T(w * l0); c.wl1[q] = T(w * l1); c.wl2[q] = T(w * l2);
+    m0 += w * l0; m1 += w * l1; m2 += w * l2;
+  }
+  c.m0 = T(m0); c.m1 = T(m1); c.m2 = T(m2);
+  return c;
+}
+
 // sin(t), cos(t) for |t| <= 0.04 (truncation < 2e-16 relative to 1)
 template <typename T>
-__device__ __forceinline__ void sincos_small(T t, T& s, T& c) {
+__device__ __forceinline__ void sincos_small(const TiledConst<T>& k, T t, T& s, T& c) {
   const T z = t * t;
-  T ps = fma(z, T(-1.0 / 5040.0), T(1.0 / 120.0));
-  ps = fma(z, ps, T(-1.0 / 6.0));
+  T ps = fma(z, k.s7, k.s5);
+  ps = fma(z, ps, k.s3);
   s = fma(t * z, ps, t);
-  T pc = fma(z, T(-1.0 / 720.0), T(1.0 / 24.0));
-  pc = fma(z, pc, T(-0.5));
+  T pc = fma(z, k.c6, k.c4);
+  pc = fma(z, pc, k.c2);
   c = fma(z, pc, T(1));
 }
 
 // sin(t), cos(t) for |t| <= 0.2 (truncation < 6e-16 relative to 1)
 template <typename T>
-__device__ __forceinline__ void sincos_medium(T t, T& s, T& c) {
+__device__ __forceinline__ void sincos_medium(const TiledConst<T>& k, T t, T& s, T& c) {
   const T z = t * t;
-  T ps = fma(z, T(1.0 / 362880.0), T(-1.0 / 5040.0));
-  ps = fma(z, ps, T(1.0 / 120.0));
-  ps = fma(z, ps, T(-1.0 / 6.0));
+  T ps = fma(z, k.s9, k.s7);
+  ps = fma(z, ps, k.s5);
+  ps = fma(z, ps, k.s3);
   s = fma(t * z, ps, t);
-  T pc = fma(z, T(-1.0 / 3628800.0), T(1.0 / 40320.0));
-  pc = fma(z, pc, T(-1.0 / 720.0));
-  pc = fma(z, pc, T(1.0 / 24.0));
-  pc = fma(z, pc, T(-0.5));
+  T pc = fma(z, k.c10, k.c8);
+  pc = fma(z, pc, k.c6);
+  pc = fma(z, pc, k.c4);
+  pc = fma(z, pc, k.c2);
   c = fma(z, pc, T(1));
 }
 
-// sin(a + t) as a polynomial in t with coefficients k[] = {sin a, cos a, -sin a/2, -cos a/6, ...}
-template <typename T, int DEG>
-__device__ __forceinline__ void shifted_sine_coefficients(T s, T c, T (&k)[DEG + 1]) {
-  constexpr double inv_fact[9] = {1.0, 1.0, -1.0 / 2.0, -1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, -1.0 / 720.0, -1.0 / 5040.0, 1.0 / 40320.0};
-#pragma unroll
-  for (int d = 0; d <= DEG; ++d) k[d] = d < 2 ? (d == 0 ? s : c) : T(inv_fact[d]) * ((d & 1) ? c : s);
-}
-
 // m_i = sum_q (w_q l_i(q)) sin(Xc + tx_q) sin(Yc + ty_q): the source about the element's CENTROID, whose
-// sin/cos (sx, cx, sy, cy) are given; u** = frequency * edge vector.  Horner of degree DEG per point; a
-// point AT the centroid (the first point of the 4-point rule) needs no polynomial at all.
+// sin/cos (sx, cx, sy, cy) are given; u** = frequency * edge vector.  Horner of degree DEG per point
+// (sin(a + t) = sum_d f[d] t^d {sin a | cos a}); a point AT the centroid (the first point of the 4-point
+// rule) needs no polynomial at all.
 template <typename T, int ORDER, int DEG>
-__device__ __forceinline__ void sinsin_moments(T sx, T cx, T sy, T cy, T uax, T ubx, T uay, T uby, T& m0, T& m1, T& m2) {
-  const TriTable tt = tri_table(ORDER);  // folded at compile time
+__device__ __forceinline__ void sinsin_moments(const TiledConst<T>& k, T sx, T cx, T sy, T cy, T uax, T ubx, T uay, T uby, T& m0, T& m1, T& m2) {
+  const TriTable tt = tri_table(ORDER);  // folded at compile time (only used to spot a point at the centroid)
   T kx[DEG + 1], ky[DEG + 1];
-  shifted_sine_coefficients<T, DEG>(sx, cx, kx);
-  shifted_sine_coefficients<T, DEG>(sy, cy, ky);
+#pragma unroll
+  for (int d = 0; d <= DEG; ++d) {
+    kx[d] = d < 2 ? (d == 0 ? sx : cx) : k.f[d] * ((d & 1) ? cx : sx);
+    ky[d] = d < 2 ? (d == 0 ? sy : cy) : k.f[d] * ((d & 1) ? cy : sy);
+  }
   m0 = m1 = m2 = T(0);
 #pragma unroll
   for (int q = 0; q < NQ<ORDER>::value; ++q) {
-    const double l1 = tt.xi[q], l2 = tt.eta[q], l0 = 1.0 - l1 - l2, w = 0.5 * tt.w[q];
-    const double c1 = l1 - 1.0 / 3.0, c2 = l2 - 1.0 / 3.0;  // barycentric offset from the centroid
+    const double o1 = tt.xi[q] - 1.0 / 3.0, o2 = tt.eta[q] - 1.0 / 3.0;
     T f;
-    if (c1 * c1 + c2 * c2 < 1e-24) {
+    if (o1 * o1 + o2 * o2 < 1e-24) {
       f = sx * sy;
     } else {
-      const T tx = fma(T(c1), uax, T(c2) * ubx), ty = fma(T(c1), uay, T(c2) * uby);
+      const T tx = fma(k.c1[q], uax, k.c2q[q] * ubx), ty = fma(k.c1[q], uay, k.c2q[q] * uby);
       T px = kx[DEG], py = ky[DEG];
 #pragma unroll
       for (int d = DEG - 1; d >= 0; --d) {
@@ -223,9 +295,9 @@ __device__ __forceinline__ void sinsin_moments(T sx, T cx, T sy, T cy, T uax, T 
       }
       f = px * py;
     }
-    m0 = fma(T(w * l0), f, m0);
-    m1 = fma(T(w * l1), f, m1);
-    m2 = fma(T(w * l2), f, m2);
+    m0 = fma(k.wl0[q], f, m0);
+    m1 = fma(k.wl1[q], f, m1);
+    m2 = fma(k.wl2[q], f, m2);
   }
 }
 
@@ -249,15 +321,18 @@ struct TiledArgs {
   const int32_t* inst_blob;
   const int4* tpl_desc;
   const int32_t* tpl_blob;
-  int max_vert, inst_words, tb_words, tc_words;
+  int max_vert, max_elem, inst_words, tb_words, tc_words;
+  int od_base[3];  // byte offsets (in units of T: already scaled) of the off-diagonal arrays inside the table
   uint32_t* progress;
   const T* coords;
-  T alpha, beta;
   SourceT<T> src;
   T* csr_val;
   T* load;
-  int key_rot_small, key_rot_medium;  // |phase base -> centroid| below: sincos_small / sincos_medium, else library
-  int key_deg4, key_deg6, key_deg8;   // element reach below: expansion degree 4 / 6 / 8, else sin() per point
+  // fast path of the source evaluation (sincos_small + degree 4) when  |phase base -> centroid| < key_rot
+  // and  max squared edge length < key_len2  (both as integer images of the thresholds); else the
+  // general path picks per warp: rotation small / medium / library, expansion degree 4 / 6 / 8 / sin() per point
+  int key_rot, key_rot_medium, key_len2;
+  int key_deg4, key_deg6, key_deg8;
 };
 
 template <int CONSUMERS>
@@ -265,28 +340,30 @@ struct MinCtas { static constexpr int value = CONSUMERS <= 256 ? 3 : 2; };
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
 __global__ void __launch_bounds__(CONSUMERS + 32, MinCtas<CONSUMERS>::value)
-assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
+assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const QuadT<T> quad) {
   constexpr int NQV = NQ<ORDER>::value;
   constexpr bool HAS_LOAD = SRC != TFEM_SRC_NONE;
   constexpr bool SINSIN = SRC == TFEM_SRC_SINSIN;
   constexpr int kWarps = CONSUMERS / 32;
+  constexpr uint32_t kRowBytes = kDlSlots * sizeof(T);
+  constexpr uint32_t kS = sizeof(T);
   using V2 = typename Vec2<T>::type;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ header | instance x3 | TB | TC | vertex coordinates x2 | table[1 + max_elem][9] ]
+  // [ header | instance x3 | TB | TC | vertex coordinates x2 | table: dl rows [2 + max_elem][6], 3 off-diagonal arrays ]
   uint64_t* inst_bar = reinterpret_cast<uint64_t*>(smem_raw);  // [3] instance landed
   uint64_t* tb_bar = inst_bar + kInstStages;                   // template part TB landed
   uint64_t* tc_bar = tb_bar + 1;                               // template part TC landed
-  uint64_t* full_bar = tc_bar + 1;                             // [2] tile staged (coords, base point, template issued)
+  uint64_t* full_bar = tc_bar + 1;                             // [2] tile staged: 32 coordinate-gather arrivals + the base point
   uint64_t* bdone_bar = full_bar + 2;                          // [2] consumers are through the integration phase
   uint64_t* done_bar = bdone_bar + 2;                          // [2] consumers finished the tile
-  int32_t* s_rec = reinterpret_cast<int32_t*>(smem_raw + 128); // [2][4] tb generation, tc generation, rotation mode
+  int32_t* s_rec = reinterpret_cast<int32_t*>(smem_raw + 128); // [2][4] tb generation, tc generation
   T* sbase = reinterpret_cast<T*>(smem_raw + 192);             // [2][8] w1*bx, w2*by, sin/cos(w1 bx), sin/cos(w2 by)
   int32_t* s_inst = reinterpret_cast<int32_t*>(smem_raw + kSmemHeader);
   int32_t* s_tb = s_inst + kInstStages * args.inst_words;
   int32_t* s_tc = s_tb + args.tb_words;
   V2* vxy = reinterpret_cast<V2*>(s_tc + args.tc_words);  // [2][max_vert]
-  T* sloc = reinterpret_cast<T*>(vxy + 2 * args.max_vert);  // [1 + max_elem][9]
+  T* sloc = reinterpret_cast<T*>(vxy + 2 * args.max_vert);  // row 0 = zeros, rows 1.. = tile elements, last row = scratch
 
   const int tid = threadIdx.x;
   // this CTA's tiles: its share of the leading (progress-reporting) tiles, dealt round-robin, then one
@@ -301,44 +378,55 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
 
   if (tid == 0) {
     for (int i = 0; i < kInstStages + 2; ++i) mbar_init(inst_bar + i, 1);  // one expect_tx arrival each
-    for (int i = 0; i < 2; ++i) mbar_init(full_bar + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(full_bar + i, 33);
     for (int i = 0; i < 2; ++i) mbar_init(bdone_bar + i, kWarps);
     for (int i = 0; i < 2; ++i) mbar_init(done_bar + i, kWarps);
     fence_mbar_init();
   }
-  if (tid < kSlots) sloc[tid] = T(0);  // row 0 of the table: the "no contribution" target of the packed codes
+  if (tid < kDlSlots) sloc[tid] = T(0);  // row 0 of the table: the "no contribution" target of the packed codes
   __syncthreads();
 
   if (tid >= CONSUMERS) {
     // =================================== producer warp =======================================
+    // Never blocks on data it fetched itself: the coordinate gather completes on the tile's `full`
+    // barrier asynchronously, the base vertex's coordinates are read one tile ahead.
     const int lane = tid - CONSUMERS;
     if (n_local == 0) return;
+    const V2* coords2 = reinterpret_cast<const V2*>(args.coords);
     auto issue_inst = [&](int it, const int4& d) {
       const int slot = it % kInstStages;
       mbar_expect_tx(inst_bar + slot, (uint32_t)d.y * 4u);
       bulk_g2s(s_inst + slot * args.inst_words, args.inst_blob + d.x, (uint32_t)d.y * 4u, inst_bar + slot);
     };
     int4 d_next = __ldg(args.tile_desc + tile_at(0));
+    V2 base_next = __ldg(coords2 + d_next.w);
     if (lane == 0) issue_inst(0, d_next);
     int cur_tpl = -1, tb_gen = 0, tc_gen = 0;
     TFEM_T_DECL;
     for (int it = 0; it < n_local; ++it) {
       const int stage = it & 1;
       const int4 d = d_next;
+      const V2 base = base_next;
       // coordinates / instance slots of tile it-2 are free once its consumers are done
       if (it >= 2) mbar_wait(done_bar + stage, ((it - 2) >> 1) & 1);
       TFEM_T(0);
       if (it + 1 < n_local) {
         d_next = __ldg(args.tile_desc + tile_at(it + 1));
         if (lane == 0) issue_inst(it + 1, d_next);
+        base_next = __ldg(coords2 + d_next.w);
       }
       mbar_wait(inst_bar + it % kInstStages, (it / kInstStages) & 1);
       TFEM_T(1);
-      const int32_t* inst = s_inst + (it % kInstStages) * args.inst_words;
-      const int n_vert = inst[0];
-      V2* dst = vxy + stage * args.max_vert;
-      for (int i = lane; i < n_vert; i += 32)
-        cp_async<(int)sizeof(V2)>(dst + i, reinterpret_cast<const V2*>(args.coords) + inst[kInstHeader + i]);
+      const uint32_t a_vert = smem_u32(s_inst + (it % kInstStages) * args.inst_words);
+      const int n_vert = (int)lds_u32(a_vert);
+      const uint32_t a_dst = smem_u32(vxy + stage * args.max_vert);
+#pragma unroll 4
+      for (int i = lane; i < n_vert; i += 32) {
+        const uint32_t v = lds_u32(a_vert + 4u * (kInstHeader + i));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(a_dst + (uint32_t)sizeof(V2) * i), "l"(coords2 + v), "n"((int)sizeof(V2)) : "memory");
+      }
+      // this lane's copies arrive on `full` when they land
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full_bar + stage)) : "memory");
       TFEM_T(2);
       if (d.z != cur_tpl) {
         // the single template buffer: TB is free after the integration phase of tile it-1, TC after
@@ -360,34 +448,23 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
         cur_tpl = d.z;
       }
       TFEM_T(3);
-      cp_async_wait_all();
-      __syncwarp();
-      int rot_mode = 0;
       if constexpr (SINSIN) {
-        // the tile's only full-range sin/cos, at its base vertex (lane 0: x phase, lane 1: y phase), and
-        // the largest phase distance of a tile vertex from it (bounds base -> centroid for every element)
-        const V2 b = dst[inst[3]];
-        const T pbx = args.src.p1 * b.x, pby = args.src.p2 * b.y;
-        int key = 0;
-        for (int i = lane; i < n_vert; i += 32) {
-          const V2 p = dst[i];
-          key = max(key, max(mag_key(fma(args.src.p1, p.x, -pbx)), mag_key(fma(args.src.p2, p.y, -pby))));
-        }
-        key = __reduce_max_sync(0xffffffffu, key);
-        rot_mode = key < args.key_rot_small ? 0 : (key < args.key_rot_medium ? 1 : 2);
-        T s, c;
-        sincos_full(lane == 0 ? pbx : pby, s, c);
-        T* sb = sbase + 8 * stage;
-        if (lane == 0) {
-          sb[0] = pbx; sb[1] = pby; sb[2] = s; sb[3] = c;
-        } else if (lane == 1) {
-          sb[4] = s; sb[5] = c;
+        // the tile's only full-range sin/cos, at its base vertex (lane 0: x phase, lane 1: y phase)
+        const T pbx = args.src.p1 * base.x, pby = args.src.p2 * base.y;
+        if (lane < 2) {
+          T s, c;
+          sincos_full(lane == 0 ? pbx : pby, s, c);
+          T* sb = sbase + 8 * stage;
+          if (lane == 0) {
+            sb[0] = pbx; sb[1] = pby; sb[2] = s; sb[3] = c;
+          } else {
+            sb[4] = s; sb[5] = c;
+          }
         }
       }
       if (lane == 0) {
         s_rec[4 * stage + 0] = tb_gen;
         s_rec[4 * stage + 1] = tc_gen;
-        s_rec[4 * stage + 2] = rot_mode;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + stage);
@@ -402,118 +479,131 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
 
   // ===================================== consumer warps ========================================
   const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t a_tab = smem_u32(sloc);
+  const uint32_t a_od0 = a_tab + (uint32_t)args.od_base[0], a_od1 = a_tab + (uint32_t)args.od_base[1], a_od2 = a_tab + (uint32_t)args.od_base[2];
+  const uint32_t a_elem = smem_u32(s_tb + kTbHeader);
   int seen_tb = 0, seen_tc = 0;
   TFEM_T_DECL;
   for (int it = 0; it < n_local; ++it) {
     const int stage = it & 1;
     mbar_wait(full_bar + stage, (it >> 1) & 1);
     TFEM_T(0);
-    const int tb_gen = s_rec[4 * stage + 0], tc_gen = s_rec[4 * stage + 1], rot_mode = s_rec[4 * stage + 2];
+    const int tb_gen = s_rec[4 * stage + 0], tc_gen = s_rec[4 * stage + 1];
     if (tb_gen != seen_tb) {  // a new template: TMA writes become visible to the threads that wait
       mbar_wait(tb_bar, (tb_gen - 1) & 1);
       seen_tb = tb_gen;
     }
     const int n_elem = s_tb[1], n_rows = s_tb[2], n_segs = s_tb[3], n_chunks = s_tb[4], n_heavy = s_tb[5], n_heavy_contrib = s_tb[6];
-    const uint32_t* elem = reinterpret_cast<const uint32_t*>(s_tb + kTbHeader);
-    const V2* xy = vxy + stage * args.max_vert;
+    const uint32_t a_xy = smem_u32(vxy + stage * args.max_vert);
     TFEM_T(1);
 
     // ---- B: local matrices and loads, each tile element once ----------------------------------
-    const TriTable tt = tri_table(ORDER);  // folded at compile time
-    const T* sb = sbase + 8 * stage;
+    const uint32_t a_sb = smem_u32(sbase + 8 * stage);
     for (int base = warp * 32; base < ((TFEM_DEBUG_SKIP & 2) ? 0 : n_elem); base += CONSUMERS) {
-      // lanes past the end recompute the last element (warp-wide reductions below need every lane)
-      const int el = min(base + lane, n_elem - 1);
-      const bool valid = base + lane < n_elem;
-      const uint32_t packed = elem[el];
-      const V2 p0 = xy[packed & 1023u], p1 = xy[(packed >> 10) & 1023u], p2 = xy[packed >> 20];
-      const T ax = p1.x - p0.x, ay = p1.y - p0.y;  // J = [[ax, bx], [ay, by]] (basis.py:87-88)
-      const T bx = p2.x - p0.x, by = p2.y - p0.y;
+      // lanes past the end recompute the last element into a scratch row (no divergence: the votes
+      // below need every lane)
+      const int el = base + lane;
+      const bool valid = el < n_elem;
+      const uint32_t packed = lds_u32(a_elem + 4u * (uint32_t)(valid ? el : n_elem - 1));
+      const uint32_t row = (uint32_t)(valid ? el + 1 : args.max_elem + 1);
+      const uint32_t out = a_tab + row * kRowBytes;
+      T x0, y0, x1, y1, x2, y2;
+      lds_2(a_xy + (packed & 1023u) * (2 * kS), x0, y0);
+      lds_2(a_xy + ((packed >> 10) & 1023u) * (2 * kS), x1, y1);
+      lds_2(a_xy + (packed >> 20) * (2 * kS), x2, y2);
+      const T ax = x1 - x0, ay = y1 - y0;  // J = [[ax, bx], [ay, by]] (basis.py:87-88)
+      const T bx = x2 - x0, by = y2 - y0;
       const T det = ax * by - bx * ay;  // signed (element_tri.py:139)
-      T* out = sloc + (el + 1) * kSlots;
+      const T s11 = fma(by, by, bx * bx), s22 = fma(ay, ay, ax * ax);  // squared edge lengths
+      T k00 = T(0), k11 = T(0), k22 = T(0), k01 = T(0), k12 = T(0), k20 = T(0), b0 = T(0), b1 = T(0), b2 = T(0);
       if constexpr (HAS_MAT) {
         // grad(phi_i) = e_i / det with e_1 = (by, -bx), e_2 = (-ay, ax), e_0 = -e_1 - e_2, so
         // sum_q dx grad(phi_i).grad(phi_j) = (wsum / det) e_i.e_j ; mass = det * reference mass
-        const T kc = (args.alpha * quad.wsum) * fast_rcp(det);
-        const T md = det * (args.beta * quad.mref[0]), mo = det * (args.beta * quad.mref[1]);
-        const T s11 = fma(by, by, bx * bx), s22 = fma(ay, ay, ax * ax), s12 = -fma(by, ay, bx * ax);
+        const T kc = cst.kcw * fast_rcp(det);
+        const T md = det * cst.md, mo = det * cst.mo;
+        const T s12 = -fma(by, ay, bx * ax);
         const T s01 = -s11 - s12, s02 = -s22 - s12, s00 = -s01 - s02;
-        if (valid) {
-          out[0] = fma(kc, s00, md);
-          out[1] = fma(kc, s11, md);
-          out[2] = fma(kc, s22, md);
-          out[3] = fma(kc, s01, mo);
-          out[4] = fma(kc, s12, mo);
-          out[5] = fma(kc, s02, mo);
-        }
+        k00 = fma(kc, s00, md);
+        k11 = fma(kc, s11, md);
+        k22 = fma(kc, s22, md);
+        k01 = fma(kc, s01, mo);
+        k12 = fma(kc, s12, mo);
+        k20 = fma(kc, s02, mo);
       }
       if constexpr (HAS_LOAD) {
-        T b0, b1, b2;
         if constexpr (SINSIN) {
           const T uax = args.src.p1 * ax, ubx = args.src.p1 * bx, uay = args.src.p2 * ay, uby = args.src.p2 * by;
           if (TFEM_DEBUG_SKIP & 16) {
             b0 = uax; b1 = ubx; b2 = uay + uby;
           } else {
-          // sin/cos of the source phase at the centroid: rotate the base vertex's values
-          const T dx = fma(args.src.p1 * T(1.0 / 3.0), (p0.x + p1.x) + p2.x, -sb[0]);
-          const T dy = fma(args.src.p2 * T(1.0 / 3.0), (p0.y + p1.y) + p2.y, -sb[1]);
-          T sx, cx, sy, cy;
-          if (rot_mode == 2) {
-            sincos_full(dx + sb[0], sx, cx);
-            sincos_full(dy + sb[1], sy, cy);
-          } else {
-            T st, ct, su, cu;
-            if (rot_mode == 0) {
-              sincos_small(dx, st, ct);
-              sincos_small(dy, su, cu);
+            // sin/cos of the source phase at the centroid: rotate the base vertex's values
+            T pbx, pby, sbx, cbx, sby, cby;
+            lds_2(a_sb, pbx, pby);
+            lds_2(a_sb + 2 * kS, sbx, cbx);
+            lds_2(a_sb + 4 * kS, sby, cby);
+            const T dx = fma(cst.w1_3, (x0 + x1) + x2, -pbx);
+            const T dy = fma(cst.w2_3, (y0 + y1) + y2, -pby);
+            const int rot = max(mag_key(dx), mag_key(dy));
+            const int len2 = max(hi_word(s11), hi_word(s22));  // non-negative: the high words order like the values
+            T sx, cx, sy, cy;
+            if (!__any_sync(0xffffffffu, (rot >= args.key_rot) | (len2 >= args.key_len2))) {
+              // every lane of the warp: small rotation, small element
+              T st, ct, su, cu;
+              sincos_small(cst, dx, st, ct);
+              sincos_small(cst, dy, su, cu);
+              sx = fma(sbx, ct, cbx * st);
+              cx = fma(cbx, ct, -(sbx * st));
+              sy = fma(sby, cu, cby * su);
+              cy = fma(cby, cu, -(sby * su));
+              sinsin_moments<T, ORDER, 4>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
             } else {
-              sincos_medium(dx, st, ct);
-              sincos_medium(dy, su, cu);
-            }
-            const T sbx = sb[2], cbx = sb[3], sby = sb[4], cby = sb[5];
-            sx = fma(sbx, ct, cbx * st);
-            cx = fma(cbx, ct, -(sbx * st));
-            sy = fma(sby, cu, cby * su);
-            cy = fma(cby, cu, -(sby * su));
-          }
-          // expansion about the centroid, degree by the largest phase any lane of the warp needs
-          const int reach = __reduce_max_sync(0xffffffffu, max(max(mag_key(uax), mag_key(ubx)), max(mag_key(uay), mag_key(uby))));
-          if (reach < args.key_deg4) {
-            sinsin_moments<T, ORDER, 4>(sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
-          } else if (reach < args.key_deg6) {
-            sinsin_moments<T, ORDER, 6>(sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
-          } else if (reach < args.key_deg8) {
-            sinsin_moments<T, ORDER, 8>(sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
-          } else {  // coarse element: evaluate the source directly
-            b0 = b1 = b2 = T(0);
+              const int rot_w = __reduce_max_sync(0xffffffffu, rot);
+              if (rot_w >= args.key_rot_medium) {
+                sincos_full(dx + pbx, sx, cx);
+                sincos_full(dy + pby, sy, cy);
+              } else {
+                T st, ct, su, cu;
+                sincos_medium(cst, dx, st, ct);
+                sincos_medium(cst, dy, su, cu);
+                sx = fma(sbx, ct, cbx * st);
+                cx = fma(cbx, ct, -(sbx * st));
+                sy = fma(sby, cu, cby * su);
+                cy = fma(cby, cu, -(sby * su));
+              }
+              // expansion about the centroid, degree by the largest phase any lane of the warp needs
+              const int reach = __reduce_max_sync(0xffffffffu, max(max(mag_key(uax), mag_key(ubx)), max(mag_key(uay), mag_key(uby))));
+              if (reach < args.key_deg4) {
+                sinsin_moments<T, ORDER, 4>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
+              } else if (reach < args.key_deg6) {
+                sinsin_moments<T, ORDER, 6>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
+              } else if (reach < args.key_deg8) {
+                sinsin_moments<T, ORDER, 8>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
+              } else {  // coarse element: evaluate the source directly
 #pragma unroll 1
-            for (int q = 0; q < NQV; ++q) {
-              const T fx = sin(args.src.p1 * fma(quad.l1[q], ax, fma(quad.l2[q], bx, p0.x)));
-              const T fy = sin(args.src.p2 * fma(quad.l1[q], ay, fma(quad.l2[q], by, p0.y)));
-              const T wf = quad.w[q] * (fx * fy);
-              b0 = fma(wf, quad.l0[q], b0);
-              b1 = fma(wf, quad.l1[q], b1);
-              b2 = fma(wf, quad.l2[q], b2);
+                for (int q = 0; q < NQV; ++q) {
+                  const T fx = sin(args.src.p1 * fma(quad.l1[q], ax, fma(quad.l2[q], bx, x0)));
+                  const T fy = sin(args.src.p2 * fma(quad.l1[q], ay, fma(quad.l2[q], by, y0)));
+                  const T wf = quad.w[q] * (fx * fy);
+                  b0 = fma(wf, quad.l0[q], b0);
+                  b1 = fma(wf, quad.l1[q], b1);
+                  b2 = fma(wf, quad.l2[q], b2);
+                }
+              }
             }
           }
-          }
-        } else {  // constant source: the moments of the basis functions are compile-time constants
-          double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-#pragma unroll
-          for (int q = 0; q < NQV; ++q) {
-            const double l1 = tt.xi[q], l2 = tt.eta[q], l0 = 1.0 - l1 - l2, w = 0.5 * tt.w[q];
-            c0 += w * l0;
-            c1 += w * l1;
-            c2 += w * l2;
-          }
-          b0 = T(c0); b1 = T(c1); b2 = T(c2);
+        } else {  // constant source: the moments of the basis functions are constants
+          b0 = cst.m0; b1 = cst.m1; b2 = cst.m2;
         }
         const T amp = args.src.p0 * det;
-        if (valid) {
-          out[6] = amp * b0;
-          out[7] = amp * b1;
-          out[8] = amp * b2;
-        }
+        b0 *= amp; b1 *= amp; b2 *= amp;
+      }
+      sts_2(out, k00, b0);
+      sts_2(out + 2 * kS, k11, b1);
+      sts_2(out + 4 * kS, k22, b2);
+      if constexpr (HAS_MAT) {
+        sts_1(a_od0 + row * kS, k01);
+        sts_1(a_od1 + row * kS, k12);
+        sts_1(a_od2 + row * kS, k20);
       }
     }
     __syncwarp();
@@ -529,16 +619,16 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
     mbar_wait(inst_bar + it % kInstStages, (it / kInstStages) & 1);  // the instance's TMA writes, for this thread
     TFEM_T(3);
     const int32_t* inst = s_inst + (it % kInstStages) * args.inst_words;
-    const int32_t* seg_start = inst + kInstHeader + pad4(inst[0]);
-    const int32_t* row_id = seg_start + pad4(n_segs);
-    const uint32_t* pair = reinterpret_cast<const uint32_t*>(s_tc);
-    const uint4* row_chunk = reinterpret_cast<const uint4*>(pair + 32 * n_segs);
-    const uint16_t* row_diag = reinterpret_cast<const uint16_t*>(row_chunk + n_chunks);
-    const uint16_t* heavy_seg = row_diag + 2 * pad4((n_rows + 1) >> 1);
+    const uint32_t a_seg = smem_u32(inst + kInstHeader + pad4(inst[0]));  // seg_start[n_segs]
+    const uint32_t a_row = a_seg + 4u * pad4(n_segs);                      // row_id[n_rows]
+    const uint32_t a_pair = smem_u32(s_tc);
+    const uint32_t a_chunk = a_pair + 128u * n_segs;
+    const uint32_t a_diag = a_chunk + 16u * n_chunks;
+    const uint16_t* heavy_seg = reinterpret_cast<const uint16_t*>(s_tc + 32 * n_segs + 4 * n_chunks + pad4((n_rows + 1) >> 1));
     const uint16_t* heavy_contrib = heavy_seg + 2 * pad4((n_heavy + 2) >> 1);
     const uint16_t* heavy_pos = heavy_contrib + 2 * pad4((n_heavy_contrib + 1) >> 1);
     auto store = [&](uint32_t code, T value) {
-      const uint32_t pos = (uint32_t)seg_start[code >> 5] + (code & 31u);
+      const uint32_t pos = lds_u32(a_seg + 4u * (code >> 5)) + (code & 31u);
       if (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30)) args.csr_val[pos] = value;
     };
     if constexpr (HAS_MAT) {
@@ -546,43 +636,56 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
       // one warp per segment of <= 32 consecutive csr_val slots (coalesced stores).  One word per lane
       // names both contributions; a missing one is code 0 (the zero row), so there is no count and no
       // inner loop.
+      T* const csr_lane = args.csr_val + lane;
+      uint32_t a_w = a_pair + 128u * warp + 4u * lane, a_s = a_seg + 4u * warp;
       constexpr int kSegUnroll = TFEM_SEG_UNROLL;
 #pragma unroll kSegUnroll
-      for (int sg = warp; sg < ((TFEM_DEBUG_SKIP & 4) ? 0 : n_segs); sg += kWarps) {
-        const uint32_t word = pair[sg * 32 + lane];
-        if (word != 0xffffffffu) {
-          const T value = sloc[word & 0xffffu] + sloc[word >> 16];
-          if (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30)) args.csr_val[(uint32_t)seg_start[sg] + lane] = value;
-        }
+      for (int sg = warp; sg < ((TFEM_DEBUG_SKIP & 4) ? 0 : n_segs); sg += kWarps, a_w += 128u * kWarps, a_s += 4u * kWarps) {
+        const uint32_t word = lds_u32(a_w);
+        const uint32_t start = lds_u32(a_s);
+        const bool mine = word != 0xffffffffu;
+        const uint32_t w = mine ? word : 0u;
+        T first, second;
+        lds_1(a_tab + code_offset<T>(w & 0xffffu), first);
+        lds_1(a_tab + code_offset<T>(w >> 16), second);
+        const T value = first + second;
+        if (mine && (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30))) csr_lane[start] = value;
       }
       TFEM_T(4);
       // the few other entries with > 2 contributions (non-manifold edges, degenerate elements)
       for (int h = tid; h < ((TFEM_DEBUG_SKIP & 4) ? 0 : n_heavy); h += CONSUMERS) {
         T acc = T(0);
-        for (int s = heavy_seg[h]; s < heavy_seg[h + 1]; ++s) acc += sloc[heavy_contrib[s]];
+        for (int s = heavy_seg[h]; s < heavy_seg[h + 1]; ++s) {
+          T v;
+          lds_1(a_tab + code_offset<T>(heavy_contrib[s]), v);
+          acc += v;
+        }
         store(heavy_pos[h], acc);
       }
     }
     // one thread per owned row: its load entry and its diagonal share one element list, read as
-    // chunks of 7 codes + link (one 16 B shared-memory load per chunk)
+    // chunks of 7 codes + link (one 16 B shared-memory load per chunk); the diagonal and the load term
+    // of an element sit side by side in the table (one 16 B load per contribution)
     for (int j = tid; j < ((TFEM_DEBUG_SKIP & 4) ? 0 : n_rows); j += CONSUMERS) {
       T rhs = T(0), diag = T(0);
       uint32_t chunk = (uint32_t)j;
       do {
-        const uint4 w = row_chunk[chunk];
+        const uint4 w = lds_v4(a_chunk + 16u * chunk);
         const uint32_t code[7] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16, w.z & 0xffffu, w.z >> 16, w.w & 0xffffu};
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
-          if constexpr (HAS_LOAD) rhs += sloc[code[k] + 6];
-          if constexpr (HAS_MAT) diag += sloc[code[k]];
+          T d, b;
+          lds_2(a_tab + code_offset<T>(code[k]), d, b);
+          diag += d;
+          rhs += b;
         }
         chunk = w.w >> 16;
       } while (chunk != 0);
       if constexpr (HAS_LOAD) {
-        if (!(TFEM_DEBUG_SKIP & 8) || rhs == T(1.2345e30)) args.load[row_id[j]] = rhs;
+        if (!(TFEM_DEBUG_SKIP & 8) || rhs == T(1.2345e30)) args.load[lds_u32(a_row + 4u * j)] = rhs;
       }
       if constexpr (HAS_MAT) {
-        const uint32_t code = row_diag[j];
+        const uint32_t code = lds_u16(a_diag + 2u * j);
         if (code != 0xffffu) store(code, diag);
       }
     }
@@ -608,12 +711,12 @@ assemble_tiled_kernel(const TiledArgs<T> args, const QuadT<T> quad) {
 }
 
 template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
-int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>& quad, cudaStream_t s) {
+int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledConst<T>& cst, const QuadT<T>& quad, cudaStream_t s) {
   args.inst_words = pad4(hp->max_inst_words);
   args.tb_words = pad4(hp->max_tb_words);
   args.tc_words = pad4(hp->max_tc_words);
   const size_t smem = kSmemHeader + 4 * ((size_t)kInstStages * args.inst_words + (size_t)args.tb_words + (size_t)args.tc_words) +
-                      sizeof(T) * ((size_t)4 * hp->max_vert + (size_t)kSlots * (hp->max_elem + 1));
+                      sizeof(T) * ((size_t)4 * hp->max_vert) + (size_t)hp->table_bytes / 8 * sizeof(T);
   if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
   auto kern = assemble_tiled_kernel<T, CONSUMERS, ORDER, SRC, HAS_MAT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -626,26 +729,26 @@ int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>& q
   int64_t resident = (int64_t)sms * per_sm;  // persistent grid: every CTA is co-resident
   if (hp->reserve_ctas > 0 && resident > hp->reserve_ctas) resident -= hp->reserve_ctas;  // room for concurrent kernels
   const unsigned grid = (unsigned)(hp->n_tiles < resident ? hp->n_tiles : resident);
-  kern<<<grid, CONSUMERS + 32, smem, s>>>(args, quad);
+  kern<<<grid, CONSUMERS + 32, smem, s>>>(args, cst, quad);
   return check_launch();
 }
 
 template <typename T, int CONSUMERS, int ORDER>
-int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const QuadT<T>& quad, cudaStream_t s) {
+int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledConst<T>& cst, const QuadT<T>& quad, cudaStream_t s) {
   const int kind = args.load ? args.src.kind : TFEM_SRC_NONE;
 #ifdef TFEM_FAST_BUILD  // experiment builds: only the headline instantiation (fp64, 4-point rule, K+M and sin-sin load)
   if constexpr (sizeof(T) == 8 && ORDER == 3) {
-    if (args.csr_val && kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, quad, s);
+    if (args.csr_val && kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, cst, quad, s);
   }
   return TFEM_ERR_UNSUPPORTED;
 #else
   if (args.csr_val) {
-    if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, quad, s);
-    if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true>(hp, args, quad, s);
-    return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_NONE, true>(hp, args, quad, s);
+    if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, cst, quad, s);
+    if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true>(hp, args, cst, quad, s);
+    return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_NONE, true>(hp, args, cst, quad, s);
   }
-  if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, false>(hp, args, quad, s);
-  if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, false>(hp, args, quad, s);
+  if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, false>(hp, args, cst, quad, s);
+  if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, false>(hp, args, cst, quad, s);
   return TFEM_ERR_BAD_ARG;
 #endif
 }
@@ -658,7 +761,11 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   if (!coords || (!csr_val && !load)) return TFEM_ERR_BAD_ARG;
   if (csr_val && !form) return TFEM_ERR_BAD_ARG;
   if (!hp->tile_list || !hp->tile_desc || !hp->inst_blob || !hp->tpl_desc || !hp->tpl_blob) return TFEM_ERR_BAD_ARG;
-  if (hp->max_vert > 1024 || hp->max_elem > 7000 || hp->max_vert < 0 || hp->max_elem < 0) return TFEM_ERR_TOO_LARGE;
+  if (hp->max_vert > 1024 || hp->max_elem > 880 || hp->max_vert < 0 || hp->max_elem < 0) return TFEM_ERR_TOO_LARGE;
+  if (hp->table_bytes > 65536 || hp->table_bytes % 16 != 0) return TFEM_ERR_BAD_ARG;
+  for (int k = 0; k < 3; ++k)
+    if (hp->od_base[k] < 48 * (hp->max_elem + 2) || hp->od_base[k] % 8 != 0 || hp->od_base[k] + 8 * (hp->max_elem + 2) > hp->table_bytes)
+      return TFEM_ERR_BAD_ARG;
   if (hp->n_tiles > kMaxIndex) return TFEM_ERR_TOO_LARGE;
   if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
   TiledArgs<T> args{};
@@ -680,16 +787,23 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   args.tpl_desc = reinterpret_cast<const int4*>(hp->tpl_desc);
   args.tpl_blob = hp->tpl_blob;
   args.max_vert = hp->max_vert;
+  args.max_elem = hp->max_elem;
+  for (int k = 0; k < 3; ++k) args.od_base[k] = hp->od_base[k] / 8 * (int)sizeof(T);
   args.coords = coords;
-  args.alpha = form ? T(form->alpha) : T(0);
-  args.beta = form ? T(form->beta) : T(0);
+  const TiledConst<T> cst = make_tiled_const<T>(quad_order, quad, form ? T(form->alpha) : T(0), form ? T(form->beta) : T(0), args.src);
   args.csr_val = csr_val;
   args.load = load;
   // accuracy thresholds of the source evaluation (see sincos_small / sincos_medium / sinsin_moments)
   const double spread = centroid_spread(quad_order);
-  args.key_rot_small = host_mag_key(0.04, T(0));
+  const double deg4_reach = 4.0e-3 / spread;  // |phase about the centroid| < 4e-3: t^5/120 < 1e-14
+  double w_max = args.src.p1 < 0 ? -(double)args.src.p1 : (double)args.src.p1;
+  const double w2_abs = args.src.p2 < 0 ? -(double)args.src.p2 : (double)args.src.p2;
+  w_max = w2_abs > w_max ? w2_abs : w_max;
+  args.key_rot = host_mag_key(0.04, T(0));
   args.key_rot_medium = host_mag_key(0.2, T(0));
-  args.key_deg4 = host_mag_key(4.0e-3 / spread, T(0));  // t^5/120 < 1e-14
+  // fast-path test on squared edge lengths: frequency * edge length < deg4_reach
+  args.key_len2 = host_mag_key(w_max > 0 ? (deg4_reach / w_max) * (deg4_reach / w_max) : 1e300, T(0));
+  args.key_deg4 = host_mag_key(deg4_reach, T(0));
   args.key_deg6 = host_mag_key(3.0e-2 / spread, T(0));  // t^7/5040 < 5e-15
   args.key_deg8 = host_mag_key(1.0e-1 / spread, T(0));  // t^9/362880 < 3e-15
   auto s = static_cast<cudaStream_t>(stream);
@@ -697,14 +811,13 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   if (consumers == 0) consumers = 384;
 #define TFEM_DISPATCH_ORDER(C)                                         \
   switch (quad_order) {                                                \
-    case 1: return dispatch_tiled<T, C, 1>(hp, args, quad, s);         \
-    case 2: return dispatch_tiled<T, C, 2>(hp, args, quad, s);         \
-    case 3: return dispatch_tiled<T, C, 3>(hp, args, quad, s);         \
-    default: return dispatch_tiled<T, C, 4>(hp, args, quad, s);        \
+    case 1: return dispatch_tiled<T, C, 1>(hp, args, cst, quad, s);         \
+    case 2: return dispatch_tiled<T, C, 2>(hp, args, cst, quad, s);         \
+    case 3: return dispatch_tiled<T, C, 3>(hp, args, cst, quad, s);         \
+    default: return dispatch_tiled<T, C, 4>(hp, args, cst, quad, s);        \
   }
   if (consumers == 256) { TFEM_DISPATCH_ORDER(256) }
   if (consumers == 384) { TFEM_DISPATCH_ORDER(384) }
-  if (consumers == 512) { TFEM_DISPATCH_ORDER(512) }
 #undef TFEM_DISPATCH_ORDER
   return TFEM_ERR_BAD_ARG;
 }

@@ -30,9 +30,90 @@ INST_HEADER_WORDS = 4
 TB_HEADER_WORDS = 8
 SEG = 32  # entries per segment: one warp pass, one lane per entry
 PER_CHUNK = 7  # contribution codes per 16 B row chunk (+ link)
-N_SLOTS = 9  # K00 K11 K22 K01 K12 K20 b0 b1 b2
+# The CTA's local table (byte offsets for fp64; the fp32 kernels halve them).  With R = max_elem + 2 rows
+# (row 0 = zeros, rows 1..n = tile elements, last row = scratch):
+#   [0, 48 R)                 "dl" rows of 48 B: {diagonal term, load term} of local vertex 0, 1, 2 -- the row
+#                             phase fetches a diagonal and its load term with one 16 B load
+#   od_base[k] + 8 row        three arrays (k = 0, 1, 2) of the off-diagonal terms K01, K12, K20
+# Consecutive rows of one array are consecutive in memory, so lanes reading the same kind of term of
+# consecutive elements never collide on a bank; the arrays' base offsets (multiples of 8 B) and the order of
+# the elements inside a tile are chosen per plan by `_choose_layout` to minimise bank conflicts.
+DL_ROW_BYTES = 48
+OD_PAD_BYTES = 128  # room behind each off-diagonal array for its base shift
 MAX_VERT = 1024  # 10-bit tile-local vertex ids
-MAX_ELEM = 7000  # 16-bit codes (element + 1) * 9 + slot
+MAX_ELEM = 880  # 16-bit byte codes: 48 R + 3 (8 R + 128) < 65536
+
+
+def table_layout(max_elem: int, shift=(0, 0, 0)):
+    """(rows R, od_base[3], table bytes) of the local table for tiles of at most `max_elem` elements."""
+    rows = max_elem + 2
+    start = DL_ROW_BYTES * rows
+    od_base = [start + k * (8 * rows + OD_PAD_BYTES) + 8 * int(shift[k]) for k in range(3)]
+    return rows, od_base, (start + 3 * (8 * rows + OD_PAD_BYTES) + 15) & ~15
+
+
+def slot_code(row: torch.Tensor, slot: torch.Tensor, od_base) -> torch.Tensor:
+    """Byte offset of local value `slot` (K00 K11 K22 K01 K12 K20 b0 b1 b2) of table row `row`."""
+    base = torch.tensor(list(od_base), dtype=torch.int64, device=row.device)
+    k = torch.where(slot >= 6, slot - 6, slot)
+    dl = DL_ROW_BYTES * row + 16 * k + 8 * (slot >= 6).long()
+    od = base[(slot - 3).clamp(0, 2)] + 8 * row
+    return torch.where((slot >= 3) & (slot < 6), od, dl)
+
+
+def _conflict_wavefronts(row, kind, active, lanes_per_group, group_bank):
+    """Wavefronts of warp-wide shared-memory loads.  row/kind/active: (n_loads, 32); a lane's address is
+    identified by (kind, row); `group_bank(kind, row)` gives its bank group (int array); lanes reading the
+    same address share a wavefront.  Loads are served per group of `lanes_per_group` lanes."""
+    import numpy as np
+
+    n = row.shape[0]
+    g = 32 // lanes_per_group
+    key = (kind.astype(np.int64) * (1 << 20) + row).reshape(n * g, lanes_per_group)
+    act = active.reshape(n * g, lanes_per_group)
+    same = key[:, :, None] == key[:, None, :]
+    earlier = np.tril(np.ones((lanes_per_group, lanes_per_group), dtype=bool), -1)
+    first = act & ~(same & earlier[None] & act[:, None, :]).any(axis=2)
+    bank = group_bank(kind, row).reshape(n * g, lanes_per_group)
+    n_banks = int(bank.max()) + 1 if bank.size else 1
+    counts = np.zeros((n * g, n_banks), dtype=np.int64)
+    np.add.at(counts, (np.repeat(np.arange(n * g), lanes_per_group).reshape(n * g, lanes_per_group)[first], bank[first]), 1)
+    return int(np.maximum(counts.max(axis=1), act.any(axis=1)).sum())
+
+
+def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_active, n_elem, max_elem):
+    """Pick the element order inside a tile and the base shifts of the off-diagonal arrays that minimise the
+    shared-memory wavefronts of the reduction phase on a representative tile.
+
+    entry_*: (2, n_segs, 32) table row (natural element order, 1-based), slot (3..5) and validity of the first /
+    second contribution of every entry lane; row_*: (n_rows, 7) of the row phase.  Returns (order, shift, stats):
+    order 1 = ascending element id, 2 = even-position elements first, then odd-position ones."""
+    import numpy as np
+
+    best = None
+    stats = {}
+    pad = (-row_rows.shape[0]) % 32
+    for order in (1, 2):
+        def remap(r):
+            loc = r - 1
+            new = np.where(loc >= 0, (loc % order) * ((n_elem + order - 1) // order) + loc // order, -1)
+            return np.where(r > 0, new + 1, 0)
+
+        rr = np.concatenate([remap(row_rows), np.zeros((pad, 7), dtype=np.int64)]).reshape(-1, 32, 7)
+        rk = np.concatenate([row_k, np.zeros((pad, 7), dtype=np.int64)]).reshape(-1, 32, 7)
+        ra = np.concatenate([row_active, np.zeros((pad, 7), dtype=bool)]).reshape(-1, 32, 7)
+        rows_wf = sum(_conflict_wavefronts(rr[:, :, j], rk[:, :, j], ra[:, :, j], 8, lambda k, r: (3 * r + k) % 8) for j in range(7))
+        er = remap(entry_rows)
+        for s1 in range(16):
+            for s2 in range(16):
+                _, od_base, _ = table_layout(max_elem, (0, s1, s2))
+                base8 = np.array(od_base) // 8
+                wf = sum(_conflict_wavefronts(er[c], entry_slots[c] - 3, entry_active[c], 16, lambda k, r: (base8[k] + r) % 16) for c in range(2))
+                if best is None or wf + rows_wf < best[0]:
+                    best = (wf + rows_wf, order, (0, s1, s2), wf, rows_wf)
+        stats[order] = rows_wf
+    return best[1], best[2], {"entries": best[3], "rows": best[4]}
+
 MAX_SEGS = 2047  # 16-bit entry codes seg * 32 + lane, 0xFFFF = none
 
 
@@ -190,7 +271,7 @@ def _hash_tiles(tile_off: torch.Tensor, blob: torch.Tensor, n_tiles: int, seed: 
     if width >= 2**14:
         raise ValueError("tile blob too long to hash")
     gen = torch.Generator(device="cpu").manual_seed(seed)
-    mult = torch.randint(1, 2**31 - 1, (4, max(width, 1)), generator=gen, dtype=torch.int64).to(device)
+    mult = torch.randint(1, 2**31 - 1, (4, max(width, 1)), generator=gen, dtype=torch.int64, device="cpu").to(device)
     word_tile = torch.repeat_interleave(torch.arange(n_tiles, device=device), per_tile)
     local = torch.arange(blob.numel(), device=device) - tile_off[word_tile]
     lo, hi = (blob & 0xFFFF) + 1, (blob >> 16) + 1
@@ -214,7 +295,7 @@ class TilePlan:
 
     n_tiles: int
     n_templates: int
-    tile_desc: torch.Tensor  # (n_tiles, 4) int32: instance word offset, instance words, template, 0
+    tile_desc: torch.Tensor  # (n_tiles, 4) int32: instance word offset, instance words, template, coords row of the base vertex
     inst_blob: torch.Tensor  # int32
     tpl_desc: torch.Tensor  # (n_templates, 4) int32: TB offset, TB words, TC offset, TC words
     tpl_blob: torch.Tensor  # int32
@@ -229,6 +310,10 @@ class TilePlan:
     halo_factor: float  # tile elements / mesh elements (1.0 = every element integrated once)
     index_bytes: int  # bytes of plan data one launch reads (instances + each template once + descriptors)
     lattice: tuple = None  # (W, bx, by) when the tiles are index-space blocks of a lattice-numbered mesh
+    table_bytes: int = 0  # bytes (fp64) of the CTA's local table
+    od_base: tuple = (0, 0, 0)  # byte offsets of the three off-diagonal arrays inside the table
+    elem_order: int = 1  # 1 = tile elements in ascending id, 2 = even positions first, then odd
+    layout_stats: dict = None  # modelled shared-memory wavefronts of the representative tile's reduction phase
     consumer_threads: int = 0  # compute threads per CTA (256 / 384 / 512); 0 = library default
     tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
     tile_list: torch.Tensor = None  # optional (n,) int32 subset / order of tiles to run (see `subset`)
@@ -245,6 +330,9 @@ class TilePlan:
         s.tpl_desc, s.tpl_blob = self.tpl_desc.data_ptr(), self.tpl_blob.data_ptr()
         s.max_vert, s.max_elem = self.max_vert, self.max_elem
         s.max_inst_words, s.max_tb_words, s.max_tc_words = self.max_inst_words, self.max_tb_words, self.max_tc_words
+        s.table_bytes = self.table_bytes
+        for k in range(3):
+            s.od_base[k] = self.od_base[k]
         s.reserve_ctas = self.reserve_ctas
         s.n_progress_tiles = self.n_progress_tiles if self.progress is not None else 0
         s.progress = None if self.progress is None else self.progress.data_ptr()
@@ -307,12 +395,58 @@ class TilePlan:
         return out
 
 
+def _layout_for_tile(t, ent_tile, ent_code, ent_cnt, c_ent, c_within, c_loc, slot, row_tile, row_ptr, lrow_cnt, lc_row, lc_within, lc_loc, lc_k,
+                     n_segs, n_rows, n_elem, max_elem):
+    """Gather tile t's reduction-phase accesses as numpy arrays and run `_choose_layout`."""
+    import numpy as np
+
+    entry_rows = np.zeros((2, n_segs * SEG), dtype=np.int64)
+    entry_slots = np.full((2, n_segs * SEG), 3, dtype=np.int64)
+    entry_active = np.zeros((2, n_segs * SEG), dtype=bool)
+    light = (ent_tile[c_ent] == t) & (ent_cnt[c_ent] <= 2) & (slot >= 3) & (slot < 6)
+    for which in (0, 1):
+        sel = light & (c_within == which)
+        code = ent_code[c_ent[sel]].cpu().numpy()
+        entry_rows[which, code] = c_loc[sel].cpu().numpy() + 1
+        entry_slots[which, code] = slot[sel].cpu().numpy()
+        entry_active[which, code] = True
+    # a lane whose entry has one contribution still reads the zero row for the other one
+    entry_active[1] |= entry_active[0]
+    row_rows = np.zeros((n_rows, PER_CHUNK), dtype=np.int64)
+    row_k = np.zeros((n_rows, PER_CHUNK), dtype=np.int64)
+    sel = (row_tile[lc_row] == t) & (lc_within < PER_CHUNK)
+    local = (lc_row[sel] - row_ptr[t]).cpu().numpy()
+    within = lc_within[sel].cpu().numpy()
+    row_rows[local, within] = lc_loc[sel].cpu().numpy() + 1
+    row_k[local, within] = lc_k[sel].cpu().numpy()
+    row_active = np.ones((n_rows, PER_CHUNK), dtype=bool)
+    return _choose_layout(entry_rows.reshape(2, n_segs, SEG), entry_slots.reshape(2, n_segs, SEG), entry_active.reshape(2, n_segs, SEG),
+                          row_rows, row_k, row_active, n_elem, max_elem)
+
+
 def default_consumers(max_elem: int) -> int:
     """Compute threads per CTA the library picks for a plan (mirrors assemble_tiled.cu)."""
     return 384
 
 
-def build_tile_plan(
+class TileTooLarge(ValueError):
+    """A tile exceeds what the kernel's 10-bit vertex ids / 16-bit table codes can address."""
+
+
+def build_tile_plan(geom_conn, dof_conn, pattern, row_points=None, rows_per_tile: int = 336, ordering: str = "auto",
+                    tile_shape: tuple | None = None) -> "TilePlan":
+    """`_build_tile_plan` with the tile size lowered until every tile fits the kernel's index widths
+    (an unstructured mesh has more elements per row than a lattice)."""
+    while True:
+        try:
+            return _build_tile_plan(geom_conn, dof_conn, pattern, row_points, rows_per_tile, ordering, tile_shape)
+        except TileTooLarge:
+            if rows_per_tile <= 8:
+                raise
+            rows_per_tile, tile_shape = max(rows_per_tile * 3 // 4, 8), None
+
+
+def _build_tile_plan(
     geom_conn: torch.Tensor,
     dof_conn: torch.Tensor,
     pattern: CsrPattern,
@@ -397,7 +531,7 @@ def build_tile_plan(
     local_v = torch.searchsorted(vert_keys, vkeys_all.reshape(-1)).reshape(-1, 3) - vert_ptr[pair_tile][:, None]
     max_vert, max_elem = int(n_v.max().item()), int(n_e.max().item())
     if max_vert > MAX_VERT or max_elem > MAX_ELEM:
-        raise ValueError(f"tile too large (vertices {max_vert} > {MAX_VERT} or elements {max_elem} > {MAX_ELEM}): lower rows_per_tile")
+        raise TileTooLarge(f"tile too large (vertices {max_vert} > {MAX_VERT} or elements {max_elem} > {MAX_ELEM}): lower rows_per_tile")
     tile_elem = local_v[:, 0] | (local_v[:, 1] << 10) | (local_v[:, 2] << 20)
     base_vertex = torch.div(n_v, 2, rounding_mode="floor")  # tile-local index of a vertex near the middle of the id range
 
@@ -425,7 +559,7 @@ def build_tile_plan(
     n_s = seg_ptr[1:] - seg_ptr[:-1]
     seg_start = whole_start[piece_run] + SEG * piece_k
     if int(n_s.max().item()) > MAX_SEGS:
-        raise ValueError("tile has too many entry segments: lower rows_per_tile")
+        raise TileTooLarge("tile has too many entry segments: lower rows_per_tile")
 
     # 5. every CSR entry of a tile (tile-ordered rows, columns ascending) with its (segment, lane)
     #    and its contributions (element ascending = reference order)
@@ -451,8 +585,8 @@ def build_tile_plan(
     c_j = coo - 9 * c_e - 3 * c_i
     slot = torch.where(c_i == c_j, c_i, 3 + (c_i + c_j == 3).long() + 2 * (c_i + c_j == 2).long())  # K00 K11 K22 K01 K12 K20
     c_tile = ent_tile[c_ent]
-    # the CTA's local table is [1 + tile elements][9]; row 0 stays zero, so code 0 = "no contribution"
-    c_code = (torch.searchsorted(pair_keys, c_tile * n_el + c_e) - elem_ptr[c_tile] + 1) * N_SLOTS + slot
+    # the CTA's local table: row 0 stays zero (code 0 = "no contribution"), row 1 + l holds the tile's l-th element
+    c_loc = torch.searchsorted(pair_keys, c_tile * n_el + c_e) - elem_ptr[c_tile]  # in ascending element id
 
     # 6. load-vector contributions per owned row
     lseg = pattern.lin_seg.long()
@@ -465,7 +599,31 @@ def build_tile_plan(
     lc_e = torch.div(lc_flat, 3, rounding_mode="floor")
     lc_k = lc_flat - 3 * lc_e
     lc_tile = row_tile[lc_row]
-    lc_code = (torch.searchsorted(pair_keys, lc_tile * n_el + lc_e) - elem_ptr[lc_tile] + 1) * N_SLOTS + lc_k
+    lc_loc = torch.searchsorted(pair_keys, lc_tile * n_el + lc_e) - elem_ptr[lc_tile]
+
+    # 6a. table layout: element order inside a tile and base shifts of the off-diagonal arrays, chosen on a
+    #     representative tile (the commonest tile shape) by counting shared-memory bank conflicts
+    order, shift, layout_stats = 1, (0, 0, 0), None
+    forced = os.environ.get("TFEM_TILE_LAYOUT")
+    if forced:
+        o, s1, s2 = (int(v) for v in forced.split(","))
+        order, shift = o, (0, s1, s2)
+    elif lattice is not None and n_el:
+        signature = (n_e * (MAX_VERT + 1) + n_r) * (MAX_SEGS + 1) + n_s
+        values, counts_sig = torch.unique(signature, return_counts=True)
+        rep_tile = int(torch.nonzero(signature == values[int(torch.argmax(counts_sig))], as_tuple=True)[0][0])
+        order, shift, layout_stats = _layout_for_tile(rep_tile, ent_tile, ent_code, ent_cnt, c_ent, c_within, c_loc, slot, row_tile, row_ptr, lrow_cnt,
+                                                      lc_row, lc_within, lc_loc, lc_k, int(n_s[rep_tile]), int(n_r[rep_tile]), int(n_e[rep_tile]), max_elem)
+    n_rows_table, od_base, table_bytes = table_layout(max_elem, shift)
+
+    def table_row(loc, tile):  # table row of the tile's loc-th element (ascending id) under the chosen order
+        per = torch.div(n_e[tile] + order - 1, order, rounding_mode="floor")
+        return (loc % order) * per + torch.div(loc, order, rounding_mode="floor") + 1
+
+    c_code = slot_code(table_row(c_loc, c_tile), slot, od_base)
+    lc_code = slot_code(table_row(lc_loc, lc_tile), lc_k, od_base)
+    elem_local = arange(pair_tile.numel()) - elem_ptr[pair_tile]
+    elem_row = table_row(elem_local, pair_tile) - 1  # position of each tile element in the TB connectivity list
 
     # 6b. who sums which entry.  One lane per entry handles entries with <= 2 contributions (every
     #     off-diagonal entry of a manifold mesh) from ONE packed word, without a loop; the diagonal of
@@ -506,7 +664,7 @@ def build_tile_plan(
     pair = first | (second << 16)
     pair[ent_cnt > 2] = 0xFFFFFFFF
 
-    # 6d. per-row chunks of 8 x u16: 7 contribution codes ((element+1)*9 + local vertex k; 0 pads) and the
+    # 6d. per-row chunks of 8 x u16: 7 contribution codes ((element+1)*80 + 16 k, k = local vertex; 0 pads) and the
     #     tile-local index of the row's next chunk (0 = none).  Chunk j < n_rows is the first chunk of
     #     row j; rows with more than 7 elements continue in chunks appended after n_rows.
     row_chunks = torch.div(lrow_cnt + PER_CHUNK - 1, PER_CHUNK, rounding_mode="floor").clamp_min(1)
@@ -548,7 +706,7 @@ def build_tile_plan(
     ]
     tb_sections = [
         header([n_v, n_e, n_r, n_s, n_ch, n_h, n_hc], TB_HEADER_WORDS),
-        _Section("elem", 32, n_e, pair_tile, arange(pair_tile.numel()) - elem_ptr[pair_tile], tile_elem),
+        _Section("elem", 32, n_e, pair_tile, elem_row, tile_elem),
     ]
     tc_sections = [
         _Section("pair", 32, n_s * SEG, ent_tile, ent_code, pair, fill=0xFFFFFFFF),
@@ -583,7 +741,9 @@ def build_tile_plan(
     tpl_blob[tb_dst] = tb_part
     tpl_blob[tc_dst] = tc_part
     tpl_desc = torch.stack([tpl_offsets[:, 0], rep_tb_words, tpl_offsets[:, 1], rep_tc_words], dim=1).to(torch.int32).contiguous()
-    tile_desc = torch.stack([inst_off[:-1], inst_words, template_of, torch.zeros_like(template_of)], dim=1).to(torch.int32).contiguous()
+    base_row = tile_vert[(vert_ptr[:-1] + base_vertex).clamp_max(max(tile_vert.numel() - 1, 0))] if tile_vert.numel() else torch.zeros_like(n_v)
+    base_row = torch.where(n_v > 0, base_row, torch.zeros_like(base_row))
+    tile_desc = torch.stack([inst_off[:-1], inst_words, template_of, base_row], dim=1).to(torch.int32).contiguous()
     default_order = torch.argsort(template_of * n_tiles + tiles).to(torch.int32).contiguous()
 
     return TilePlan(
@@ -605,4 +765,8 @@ def build_tile_plan(
         index_bytes=4 * (inst_blob.numel() + tpl_blob.numel() + tile_desc.numel() + tpl_desc.numel() + default_order.numel()),
         lattice=lattice,
         tile_of_row=tile_of_row,
+        table_bytes=table_bytes,
+        od_base=tuple(od_base),
+        elem_order=order,
+        layout_stats=layout_stats,
     )

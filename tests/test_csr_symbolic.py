@@ -60,7 +60,7 @@ def test_kat_pattern_4x4():
 
 
 @pytest.mark.parametrize("name,mesh", list(meshes()))
-@pytest.mark.parametrize("rows_per_tile,ordering", [(8, "block"), (16, "morton"), (7, "natural"), (256, "block")])
+@pytest.mark.parametrize("rows_per_tile,ordering", [(8, "block"), (16, "morton"), (7, "natural"), (256, "block"), (48, "auto")])
 def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
     coords, conn = mesh["vertices"], mesh["triangles"]
     n_dof = coords.shape[0]
@@ -86,3 +86,23 @@ def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
     # every row is owned by exactly one tile
     owned = np.concatenate([plan.sections(t)["row_id"] for t in range(plan.n_tiles)])
     assert sorted(owned.tolist()) == list(range(n_dof))
+
+
+def test_lattice_plan_shares_templates_and_picks_a_layout():
+    """A lattice-numbered mesh is tiled in index space (independent of the jitter): congruent tiles share
+    one template, and the table layout search beats the plain layout in the bank-conflict model."""
+    from pytorch_fem_solver_b200 import tileplan
+
+    mesh = meshgen.structured_rectangle(96, 64, jitter=0.25, seed=5, topology=False)
+    conn = torch.from_numpy(mesh["triangles"])
+    pat = csr.build_pattern(conn, mesh["vertices"].shape[0])
+    assert tileplan.detect_lattice(pat) == 97
+    plan = csr.build_tile_plan(conn, conn, pat, torch.from_numpy(mesh["vertices"]), 96, "auto", tile_shape=(12, 8))
+    assert plan.lattice == (97, 12, 8)
+    assert plan.n_templates <= 16 < plan.n_tiles  # interior + edge / corner shapes only
+    populations = torch.bincount(plan.tile_desc[:, 2].long())
+    assert int(populations.max()) >= (96 // 12 - 2) * (64 // 8 - 2)
+    assert plan.layout_stats is not None and plan.elem_order in (1, 2)
+    # an unstructured mesh is not mistaken for a lattice
+    other = meshgen.delaunay_unit_square(300, seed=1)
+    assert tileplan.detect_lattice(csr.build_pattern(torch.from_numpy(other["triangles"]), other["vertices"].shape[0])) == 0

@@ -109,11 +109,10 @@ def main():
                     table = (ctypes.c_longlong * 16)()
                     ctas = ctypes.c_int()
                     timing(table, ctypes.byref(ctas))
-                    n = max(ctas.value, 1) * args.steps / max(args.steps, 1)
-                    prod = [table[i] / max(ctas.value, 1) / args.steps for i in range(8)]
-                    cons = [table[8 + i] / max(ctas.value, 1) / args.steps for i in range(8)]
-                    print("    producer cycles/CTA/launch: wait done %.0f | wait inst %.0f | issue gather %.0f | template %.0f | landed+base %.0f" % tuple(prod[:5]))
-                    print("    consumer cycles/CTA/launch: wait full %.0f | header %.0f | B+sync %.0f | wait TC/inst %.0f | C entries %.0f | C rows %.0f | end sync %.0f" % tuple(cons[:7]))
+                    prod = [table[i] / max(ctas.value, 1) for i in range(8)]  # the CTA counter grows by one per CTA per launch
+                    cons = [table[8 + i] / max(ctas.value, 1) for i in range(8)]
+                    print("    producer cycles/CTA/launch: wait done %.0f | wait inst %.0f | issue gather %.0f | template %.0f | base+arrive %.0f" % tuple(prod[:5]))
+                    print("    consumer thread 0 cycles/CTA/launch: wait full+header %.0f | B %.0f | wait TC/inst %.0f | C entries %.0f | C rows %.0f | barrier %.0f" % tuple(cons[:6]))
 
 
 if __name__ == "__main__":
