@@ -61,6 +61,10 @@ __device__ int tfem_timing_ctas;
 #define TFEM_T(i)
 #endif
 
+#ifdef TFEM_STAGGER_NS
+__device__ int tfem_stagger_slots[1024];
+#endif
+
 namespace tfem {
 
 // ---- mbarrier / TMA bulk-copy / cp.async wrappers (PTX ISA 8.x, sm_90+) ---------------------
@@ -119,9 +123,10 @@ __device__ __forceinline__ void consumer_sync() {
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
 constexpr int kInstHeader = 4;
 constexpr int kTbHeader = 8;
-constexpr int kInstStages = 3;    // instance blobs in flight
+constexpr int kInstStages = 4;    // instance blobs in flight: tile t+1 prefetched, t being staged, t-1 and t-2 with the consumers
 constexpr int kDlSlots = 6;       // one "dl" table row per tile element: d0 b0 d1 b1 d2 b2 (include/tfem_b200.h)
-constexpr int kSmemHeader = 384;  // mbarriers, two stage records, two base-point records
+constexpr int kStages = 3;        // tiles staged ahead of the consumers (coordinates, record, base point)
+constexpr int kSmemHeader = 512;  // mbarriers, stage records, base-point records
 
 // ---- shared-memory accesses by 32-bit address (no generic-pointer arithmetic in the hot loops) --
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -137,6 +142,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4i(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ void lds_2(uint32_t a, double& x, double& y) {
@@ -211,6 +221,8 @@ struct TiledConst {
   T c1[kMaxQ], c2q[kMaxQ];      // barycentric offsets of the quadrature points from the centroid
   T wl0[kMaxQ], wl1[kMaxQ], wl2[kMaxQ];  // w_q * l_i(q)
   T m0, m1, m2;                 // sum_q w_q l_i(q)  (constant source)
+  T o3_w1, o3_w2;               // 4-point rule: source frequencies * 2/15 (offsets of its outer points from the centroid)
+  T o3_a, o3_b, o3_c;           // 4-point rule: w_c / 3, w_o / 5, 2 w_o / 5
 };
 
 template <typename T>
@@ -235,6 +247,11 @@ TiledConst<T> make_tiled_const(int order, const QuadT<T>& quad, T alpha, T beta,
     m0 += w * l0; m1 += w * l1; m2 += w * l2;
   }
   c.m0 = T(m0); c.m1 = T(m1); c.m2 = T(m2);
+  c.o3_w1 = T(double(src.p1) * 2.0 / 15.0);
+  c.o3_w2 = T(double(src.p2) * 2.0 / 15.0);
+  c.o3_a = T(0.5 * (-9.0 / 16.0) / 3.0);
+  c.o3_b = T(0.5 * (25.0 / 48.0) / 5.0);
+  c.o3_c = T(0.5 * (25.0 / 48.0) * 2.0 / 5.0);
   return c;
 }
 
@@ -301,6 +318,25 @@ __device__ __forceinline__ void sinsin_moments(const TiledConst<T>& k, T sx, T c
   }
 }
 
+// The same moments for the 4-point rule (element_tri.py:99-108: centroid, weight -9/16, and the three points
+// centroid + 2/5 (vertex - centroid), weight 25/48) with its structure spelled out: the outer points' phases are
+// 2 va - vb, 2 vb - va, -(va + vb) with v = 2/15 frequency * edge, and m_i = a f_c + b (f_1 + f_2 + f_3) + c f_i'.
+// 17 fp64 operations and 20 constants fewer than the table-driven form; degree 4 (|phase| < 4e-3).
+template <typename T>
+__device__ __forceinline__ void sinsin_moments_o3(const TiledConst<T>& k, T sx, T cx, T sy, T cy, T ax, T bx, T ay, T by, T& m0, T& m1, T& m2) {
+  const T vax = k.o3_w1 * ax, vbx = k.o3_w1 * bx, vay = k.o3_w2 * ay, vby = k.o3_w2 * by;
+  const T kx2 = k.f[2] * sx, kx3 = k.f[3] * cx, kx4 = k.f[4] * sx;
+  const T ky2 = k.f[2] * sy, ky3 = k.f[3] * cy, ky4 = k.f[4] * sy;
+  auto shifted = [](T t, T k0, T k1, T k2, T k3, T k4) { return fma(fma(fma(fma(k4, t, k3), t, k2), t, k1), t, k0); };
+  const T f1 = shifted(fma(T(2), vax, -vbx), sx, cx, kx2, kx3, kx4) * shifted(fma(T(2), vay, -vby), sy, cy, ky2, ky3, ky4);  // l = (.2, .6, .2)
+  const T f2 = shifted(fma(T(2), vbx, -vax), sx, cx, kx2, kx3, kx4) * shifted(fma(T(2), vby, -vay), sy, cy, ky2, ky3, ky4);  // l = (.2, .2, .6)
+  const T f3 = shifted(-(vax + vbx), sx, cx, kx2, kx3, kx4) * shifted(-(vay + vby), sy, cy, ky2, ky3, ky4);                  // l = (.6, .2, .2)
+  const T common = fma(k.o3_b, (f1 + f2) + f3, k.o3_a * (sx * sy));
+  m0 = fma(k.o3_c, f3, common);
+  m1 = fma(k.o3_c, f1, common);
+  m2 = fma(k.o3_c, f2, common);
+}
+
 // largest |barycentric offset| sum over the rule's points: |phase about the centroid| <= this * reach
 inline double centroid_spread(int order) {
   const TriTable tt = tri_table(order);
@@ -350,20 +386,22 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
   using V2 = typename Vec2<T>::type;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // [ header | instance x3 | TB | TC | vertex coordinates x2 | table: dl rows [2 + max_elem][6], 3 off-diagonal arrays ]
-  uint64_t* inst_bar = reinterpret_cast<uint64_t*>(smem_raw);  // [3] instance landed
+  // [ header | instance x4 | TB | TC | vertex coordinates x3 | table: dl rows [2 + max_elem][6], 3 off-diagonal arrays ]
+  uint64_t* inst_bar = reinterpret_cast<uint64_t*>(smem_raw);  // [4] instance landed
   uint64_t* tb_bar = inst_bar + kInstStages;                   // template part TB landed
   uint64_t* tc_bar = tb_bar + 1;                               // template part TC landed
-  uint64_t* full_bar = tc_bar + 1;                             // [2] tile staged: 32 coordinate-gather arrivals + the base point
-  uint64_t* bdone_bar = full_bar + 2;                          // [2] consumers are through the integration phase
-  uint64_t* done_bar = bdone_bar + 2;                          // [2] consumers finished the tile
-  int32_t* s_rec = reinterpret_cast<int32_t*>(smem_raw + 128); // [2][4] tb generation, tc generation
-  T* sbase = reinterpret_cast<T*>(smem_raw + 192);             // [2][8] w1*bx, w2*by, sin/cos(w1 bx), sin/cos(w2 by)
+  uint64_t* full_bar = tc_bar + 1;                             // [3] tile staged: 32 coordinate-gather arrivals + the record
+  uint64_t* bdone_bar = full_bar + kStages;                    // [3] consumers are through the integration phase
+  uint64_t* done_bar = bdone_bar + kStages;                    // [3] consumers finished the tile
+  // [3][8] record of a staged tile, written by the producer: template generation, n_vert, n_elem, n_rows,
+  // n_segs, n_chunks, n_heavy, n_heavy_contrib -- everything the consumers need, in two 16 B loads
+  int32_t* s_rec = reinterpret_cast<int32_t*>(smem_raw + 128);
+  T* sbase = reinterpret_cast<T*>(smem_raw + 256);             // [3][8] w1*bx, w2*by, sin/cos(w1 bx), sin/cos(w2 by)
   int32_t* s_inst = reinterpret_cast<int32_t*>(smem_raw + kSmemHeader);
   int32_t* s_tb = s_inst + kInstStages * args.inst_words;
   int32_t* s_tc = s_tb + args.tb_words;
-  V2* vxy = reinterpret_cast<V2*>(s_tc + args.tc_words);  // [2][max_vert]
-  T* sloc = reinterpret_cast<T*>(vxy + 2 * args.max_vert);  // row 0 = zeros, rows 1.. = tile elements, last row = scratch
+  V2* vxy = reinterpret_cast<V2*>(s_tc + args.tc_words);  // [3][max_vert]
+  T* sloc = reinterpret_cast<T*>(vxy + kStages * args.max_vert);  // row 0 = zeros, rows 1.. = tile elements, last row = scratch
 
   const int tid = threadIdx.x;
   // this CTA's tiles: its share of the leading (progress-reporting) tiles, dealt round-robin, then one
@@ -378,9 +416,9 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
 
   if (tid == 0) {
     for (int i = 0; i < kInstStages + 2; ++i) mbar_init(inst_bar + i, 1);  // one expect_tx arrival each
-    for (int i = 0; i < 2; ++i) mbar_init(full_bar + i, 33);
-    for (int i = 0; i < 2; ++i) mbar_init(bdone_bar + i, kWarps);
-    for (int i = 0; i < 2; ++i) mbar_init(done_bar + i, kWarps);
+    for (int i = 0; i < kStages; ++i) mbar_init(full_bar + i, 33);
+    for (int i = 0; i < kStages; ++i) mbar_init(bdone_bar + i, kWarps);
+    for (int i = 0; i < kStages; ++i) mbar_init(done_bar + i, kWarps);
     fence_mbar_init();
   }
   if (tid < kDlSlots) sloc[tid] = T(0);  // row 0 of the table: the "no contribution" target of the packed codes
@@ -401,14 +439,15 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
     int4 d_next = __ldg(args.tile_desc + tile_at(0));
     V2 base_next = __ldg(coords2 + d_next.w);
     if (lane == 0) issue_inst(0, d_next);
-    int cur_tpl = -1, tb_gen = 0, tc_gen = 0;
+    int cur_tpl = -1, gen = 0;
+    int4 head_a = make_int4(0, 0, 0, 0), head_b = make_int4(0, 0, 0, 0);  // TB header of the resident template
     TFEM_T_DECL;
     for (int it = 0; it < n_local; ++it) {
-      const int stage = it & 1;
+      const int stage = it % kStages, round = it / kStages;
       const int4 d = d_next;
       const V2 base = base_next;
-      // coordinates / instance slots of tile it-2 are free once its consumers are done
-      if (it >= 2) mbar_wait(done_bar + stage, ((it - 2) >> 1) & 1);
+      // the coordinates and the instance slot of tile it-3 are free once that tile is done
+      if (it >= kStages) mbar_wait(done_bar + stage, (round - 1) & 1);
       TFEM_T(0);
       if (it + 1 < n_local) {
         d_next = __ldg(args.tile_desc + tile_at(it + 1));
@@ -433,18 +472,22 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
         // its reduction phase.  Rare on lattice meshes (a CTA's tiles are congruent); on an
         // unstructured mesh every tile brings its own template and this is the steady state.
         const int4 td = __ldg(args.tpl_desc + d.z);
-        if (it >= 1) mbar_wait(bdone_bar + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        if (it >= 1) mbar_wait(bdone_bar + (it - 1) % kStages, ((it - 1) / kStages) & 1);
         if (lane == 0) {
           mbar_expect_tx(tb_bar, (uint32_t)td.y * 4u);
           bulk_g2s(s_tb, args.tpl_blob + td.x, (uint32_t)td.y * 4u, tb_bar);
         }
-        if (it >= 1) mbar_wait(done_bar + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        if (it >= 1) mbar_wait(done_bar + (it - 1) % kStages, ((it - 1) / kStages) & 1);
         if (lane == 0) {
           mbar_expect_tx(tc_bar, (uint32_t)td.w * 4u);
           bulk_g2s(s_tc, args.tpl_blob + td.z, (uint32_t)td.w * 4u, tc_bar);
         }
-        ++tb_gen;
-        ++tc_gen;
+        // the consumers read the template's header from the tile record: wait for TB here (they then need
+        // no wait of their own for it: this thread's arrival on `full` orders the TMA writes before them)
+        mbar_wait(tb_bar, gen & 1);
+        head_a = lds_v4i(smem_u32(s_tb));
+        head_b = lds_v4i(smem_u32(s_tb) + 16u);
+        ++gen;
         cur_tpl = d.z;
       }
       TFEM_T(3);
@@ -463,8 +506,9 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
         }
       }
       if (lane == 0) {
-        s_rec[4 * stage + 0] = tb_gen;
-        s_rec[4 * stage + 1] = tc_gen;
+        int4* rec = reinterpret_cast<int4*>(s_rec + 8 * stage);
+        rec[0] = make_int4(gen, n_vert, head_a.y, head_a.z);          // generation, n_vert, n_elem, n_rows
+        rec[1] = make_int4(head_a.w, head_b.x, head_b.y, head_b.z);  // n_segs, n_chunks, n_heavy, n_heavy_contrib
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar + stage);
@@ -479,21 +523,37 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
 
   // ===================================== consumer warps ========================================
   const int lane = tid & 31, warp = tid >> 5;
+#ifdef TFEM_STAGGER_NS
+  // experiment: the second CTA to arrive on an SM starts late, so that one CTA integrates (fp64 pipe)
+  // while the other reduces (shared-memory pipe)
+  {
+    __shared__ int s_arrival;
+    if (tid == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      s_arrival = atomicAdd(&tfem_stagger_slots[smid], 1);
+    }
+    consumer_sync<CONSUMERS>();
+    if (s_arrival & 1) {
+      const uint64_t t0 = global_timer_ns();
+      while (global_timer_ns() - t0 < TFEM_STAGGER_NS) __nanosleep(100);
+    }
+  }
+#endif
   const uint32_t a_tab = smem_u32(sloc);
   const uint32_t a_od0 = a_tab + (uint32_t)args.od_base[0], a_od1 = a_tab + (uint32_t)args.od_base[1], a_od2 = a_tab + (uint32_t)args.od_base[2];
   const uint32_t a_elem = smem_u32(s_tb + kTbHeader);
-  int seen_tb = 0, seen_tc = 0;
+  int seen_tc = 0;
   TFEM_T_DECL;
   for (int it = 0; it < n_local; ++it) {
-    const int stage = it & 1;
-    mbar_wait(full_bar + stage, (it >> 1) & 1);
+    const int stage = it % kStages, round = it / kStages;
+    mbar_wait(full_bar + stage, round & 1);
     TFEM_T(0);
-    const int tb_gen = s_rec[4 * stage + 0], tc_gen = s_rec[4 * stage + 1];
-    if (tb_gen != seen_tb) {  // a new template: TMA writes become visible to the threads that wait
-      mbar_wait(tb_bar, (tb_gen - 1) & 1);
-      seen_tb = tb_gen;
-    }
-    const int n_elem = s_tb[1], n_rows = s_tb[2], n_segs = s_tb[3], n_chunks = s_tb[4], n_heavy = s_tb[5], n_heavy_contrib = s_tb[6];
+    // everything about the tile in two 16 B loads (the producer's arrival on `full` also orders the TMA
+    // writes of the instance and of a new TB part before this point)
+    const int4 rec_a = lds_v4i(smem_u32(s_rec + 8 * stage)), rec_b = lds_v4i(smem_u32(s_rec + 8 * stage) + 16u);
+    const int tc_gen = rec_a.x, n_vert = rec_a.y, n_elem = rec_a.z, n_rows = rec_a.w;
+    const int n_segs = rec_b.x, n_chunks = rec_b.y, n_heavy = rec_b.z, n_heavy_contrib = rec_b.w;
     const uint32_t a_xy = smem_u32(vxy + stage * args.max_vert);
     TFEM_T(1);
 
@@ -555,7 +615,8 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
               cx = fma(cbx, ct, -(sbx * st));
               sy = fma(sby, cu, cby * su);
               cy = fma(cby, cu, -(sby * su));
-              sinsin_moments<T, ORDER, 4>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
+              if constexpr (ORDER == 3) sinsin_moments_o3<T>(cst, sx, cx, sy, cy, ax, bx, ay, by, b0, b1, b2);
+              else sinsin_moments<T, ORDER, 4>(cst, sx, cx, sy, cy, uax, ubx, uay, uby, b0, b1, b2);
             } else {
               const int rot_w = __reduce_max_sync(0xffffffffu, rot);
               if (rot_w >= args.key_rot_medium) {
@@ -612,14 +673,13 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
     TFEM_T(2);
 
     // ---- C: one lane per CSR entry / one thread per row; contributions in increasing element id --
-    if (tc_gen != seen_tc) {
+    if (tc_gen != seen_tc) {  // a new template: its TC part may still be in flight
       mbar_wait(tc_bar, (tc_gen - 1) & 1);
       seen_tc = tc_gen;
     }
-    mbar_wait(inst_bar + it % kInstStages, (it / kInstStages) & 1);  // the instance's TMA writes, for this thread
     TFEM_T(3);
     const int32_t* inst = s_inst + (it % kInstStages) * args.inst_words;
-    const uint32_t a_seg = smem_u32(inst + kInstHeader + pad4(inst[0]));  // seg_start[n_segs]
+    const uint32_t a_seg = smem_u32(inst + kInstHeader + pad4(n_vert));  // seg_start[n_segs]
     const uint32_t a_row = a_seg + 4u * pad4(n_segs);                      // row_id[n_rows]
     const uint32_t a_pair = smem_u32(s_tc);
     const uint32_t a_chunk = a_pair + 128u * n_segs;
@@ -643,13 +703,13 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
       for (int sg = warp; sg < ((TFEM_DEBUG_SKIP & 4) ? 0 : n_segs); sg += kWarps, a_w += 128u * kWarps, a_s += 4u * kWarps) {
         const uint32_t word = lds_u32(a_w);
         const uint32_t start = lds_u32(a_s);
-        const bool mine = word != 0xffffffffu;
-        const uint32_t w = mine ? word : 0u;
-        T first, second;
-        lds_1(a_tab + code_offset<T>(w & 0xffffu), first);
-        lds_1(a_tab + code_offset<T>(w >> 16), second);
-        const T value = first + second;
-        if (mine && (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30))) csr_lane[start] = value;
+        if (word != 0xffffffffu) {  // lanes without an entry issue no table load (they would only add bank conflicts)
+          T first, second;
+          lds_1(a_tab + code_offset<T>(word & 0xffffu), first);
+          lds_1(a_tab + code_offset<T>(word >> 16), second);
+          const T value = first + second;
+          if (!(TFEM_DEBUG_SKIP & 8) || value == T(1.2345e30)) csr_lane[start] = value;
+        }
       }
       TFEM_T(4);
       // the few other entries with > 2 contributions (non-manifold edges, degenerate elements)
@@ -716,7 +776,7 @@ int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledConst<
   args.tb_words = pad4(hp->max_tb_words);
   args.tc_words = pad4(hp->max_tc_words);
   const size_t smem = kSmemHeader + 4 * ((size_t)kInstStages * args.inst_words + (size_t)args.tb_words + (size_t)args.tc_words) +
-                      sizeof(T) * ((size_t)4 * hp->max_vert) + (size_t)hp->table_bytes / 8 * sizeof(T);
+                      sizeof(T) * ((size_t)2 * kStages * hp->max_vert) + (size_t)hp->table_bytes / 8 * sizeof(T);
   if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
   auto kern = assemble_tiled_kernel<T, CONSUMERS, ORDER, SRC, HAS_MAT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

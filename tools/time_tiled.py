@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--ny", type=int, default=1024)
     ap.add_argument("--check", action="store_true", help="compare every build's output with the first one")
+    ap.add_argument("--reserve", type=int, default=0, help="CTA slots left free (148 = one CTA per SM)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     mesh = meshgen.structured_rectangle(args.nx, args.ny, jitter=0.25, seed=1234, topology=False)
@@ -67,6 +68,7 @@ def main():
         for shape, plan in plans.items():
             for consumers in (int(c) for c in args.consumers.split(",")):
                 plan.consumer_threads = consumers
+                plan.reserve_ctas = args.reserve
                 struct = plan.c_struct()
 
                 def launch():
