@@ -112,7 +112,6 @@ def header_symbols() -> list[str]:
 
 
 _lib = None
-_tls = threading.local()  # cudaSetDevice is per host thread (autograd runs backward on its own)
 
 
 def load() -> ctypes.CDLL:
@@ -184,11 +183,10 @@ def call(base: str, dtype: torch.dtype | None, device: torch.device, *args):
     """Invoke `base_{f64|f32}` on the current stream of `device`; raise on a negative status."""
     lib = load()
     index = device.index if device.index is not None else torch.cuda.current_device()
-    if getattr(_tls, "device", None) != index:
-        status = lib.tfem_set_device(index)
-        if status != 0:
-            raise TfemError(f"tfem_set_device({index}) failed")
-        _tls.device = index
+    # every call: the library links the static CUDA runtime but shares the thread's current context with torch,
+    # so another `torch.cuda.set_device` / `torch.cuda.device(...)` on this thread would invalidate a cached choice
+    if lib.tfem_set_device(index) != 0:
+        raise TfemError(f"tfem_set_device({index}) failed")
     name = base if dtype is None else f"{base}_{suffix(dtype)}"
     stream = torch.cuda.current_stream(device).cuda_stream
     status = getattr(lib, name)(*args, stream)

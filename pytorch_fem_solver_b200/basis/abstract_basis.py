@@ -218,7 +218,7 @@ class AbstractBasis(abc.ABC):
             if src.kind == ops.SRC_SAMPLED:
                 f_q = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
             vec = ops.weak_residual(
-                grad.to(self.dtype).reshape(lay.n_total, self.n_q, lay.d).contiguous(), lay.coords, lay.conn,
+                grad.to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous(), lay.coords, lay.conn,
                 self._dof_conn_flat(), pat.lin_seg, pat.lin_perm, lay.n_el_per_mesh, lay.n_vert_per_mesh,
                 self._element.integration_order, src.kind, list(src.params), f_q, *lay.frac_args(),
             )

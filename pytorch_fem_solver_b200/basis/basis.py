@@ -102,7 +102,7 @@ class Basis(AbstractBasis):
             raise NotImplementedError("Interpolation for this basis not implemented")
         if tensor is not None:
             return self._interpolate_values(basis, tensor)
-        nodes = self._interpolation_nodes()
+        nodes = self._interpolation_nodes(basis)
 
         def interpolator(function: Callable[[torch.Tensor], torch.Tensor]) -> torch.Tensor:
             return self._interpolate_values(basis, function(nodes))[0]
@@ -112,5 +112,5 @@ class Basis(AbstractBasis):
 
         return interpolator, interpolator_grad
 
-    def _interpolation_nodes(self):
+    def _interpolation_nodes(self, basis=None):
         return self._coords4global_dofs

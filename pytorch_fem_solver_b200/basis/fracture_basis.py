@@ -124,5 +124,10 @@ class FractureBasis(Basis):
         # (fracture_basis.py:229-231 gathers mesh["cells","vertices"]); kept for parity
         return cells.to(torch.int32).reshape(-1, 2).contiguous(), lay.conn, first, inv, x_q, n_edge_per_mesh, lay.n_el_per_mesh
 
-    def _interpolation_nodes(self):
+    def _interpolation_nodes(self, basis=None):
+        # own quadrature points: the interpolant gathers with the GLOBAL (glued) DOF ids, so the function is
+        # evaluated at the global representative vertices.  Towards the edges the reference indexes the nodal
+        # vector with fracture-LOCAL vertex ids (fracture_basis.py:229-231), kept as is.
+        if basis is self:
+            return self.global_triangulation["vertices_3D"]
         return self.mesh["vertices", "coordinates_3d"]

@@ -322,6 +322,19 @@ class PeerExchange:
                 ops.pack_after_raw(halves[half], buffer, idx, progress, target)
             self.handle.put_signal(owner, self.DATA + half, self.timeout_ms)
 
+    def wait_local(self, buffer: torch.Tensor, progress: torch.Tensor, target: int):
+        """Order this stream after the interface tiles of the assembly launch running beside it, on a rank
+        that only RECEIVES (a rank that sends is already ordered by its pack kernels, which wait for the
+        same counter): without it the owner's add could race with its own tiles' plain stores."""
+        if self.sends or not self.recvs:
+            return
+        from . import ops
+
+        if getattr(self, "_wait_scratch", None) is None:
+            self._wait_scratch = torch.zeros(1, dtype=buffer.dtype, device=buffer.device)
+            self._wait_index = torch.zeros(1, dtype=torch.int32, device=buffer.device)
+        ops.pack_after_raw(self._wait_scratch, buffer, self._wait_index, progress, target)
+
     def gather_add(self, buffer: torch.Tensor):
         half = self.steps & 1
         for peer, idx, halves in self.recvs:  # ascending peer order -> bitwise reproducible sums
@@ -427,10 +440,16 @@ class StripAssembly:
             # counter; the pack kernels on the side stream wait for that counter, store over NVLink
             # into the owners' buffers and signal, while the same launch goes on with the interior
             self.progress_target += self.n_interface_tiles * self.ordered_tiles.consumer_warps
+            # everything the calling stream has waited for so far (the previous step, and in the host pipeline
+            # the copies that free `coords` / `buffer`) also gates the side stream
+            entered = torch.cuda.Event()
+            entered.record(main)
             self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
             with torch.cuda.stream(self.side_stream):
                 self.side_stream.wait_event(self._previous_step)  # the buffer's previous contents are final
+                self.side_stream.wait_event(entered)
                 self.fused_exchange.pack(buffer, self.progress, self.progress_target)
+                self.fused_exchange.wait_local(buffer, self.progress, self.progress_target)
                 self.fused_exchange.gather_add(buffer)
                 finished = torch.cuda.Event()
                 finished.record(self.side_stream)

@@ -61,7 +61,7 @@ class AbstractMesh(abc.ABC):
             return False
         if isinstance(key, tuple):
             return key[0] in _LAZY_GROUPS or key == ("cells", "length") or key[0] == "edges"
-        return key in _LAZY_GROUPS or key == "edges"
+        return key in _LAZY_GROUPS or key in ("edges", "cells")
 
     def __getitem__(self, key):
         if self._needs_topology(key):
@@ -72,6 +72,8 @@ class AbstractMesh(abc.ABC):
         self._triangulation[key] = value
 
     def __contains__(self, key):
+        if self._needs_topology(key):
+            self._build_optional_parameters()
         return key in self._triangulation
 
     def batch_size(self):
@@ -91,6 +93,17 @@ class AbstractMesh(abc.ABC):
         """Move every tensor of the mesh (in place) and return self."""
         self._triangulation = self._triangulation.to(device)
         return self
+
+    def copy_to(self, device) -> "AbstractMesh":
+        """A copy of the mesh on `device`; the caller's object (and its tensors) stay where they are."""
+        import copy
+
+        other = copy.copy(self)
+        other._triangulation = self._triangulation.to(device)
+        for name, value in vars(self).items():  # tensor attributes of subclasses (Patches: centers, radius, ...)
+            if isinstance(value, torch.Tensor):
+                setattr(other, name, value.to(device))
+        return other
 
     # ---- construction ------------------------------------------------------------------------
     def _triangle_to_tensordict(self, mesh_dict) -> TensorDict:

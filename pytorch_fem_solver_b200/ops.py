@@ -646,4 +646,5 @@ def place_mesh(mesh):
             "pytorch_fem_solver_b200 needs a CUDA device: the element-assembly path has no CPU implementation"
         )
     _lib.load()  # fail now, not at the first integrate_* call, if the library is missing
-    return mesh.to(torch.device("cuda", torch.cuda.current_device()))
+    # a copy: building a basis must not turn the caller's CPU mesh into a CUDA mesh behind their back
+    return mesh.copy_to(torch.device("cuda", torch.cuda.current_device()))

@@ -77,7 +77,12 @@ def cg(
     b_norm = float(torch.linalg.vector_norm(b))
     if b_norm == 0.0:
         return x, CgInfo(0, 0.0, True)
-    limit = max_iterations if max_iterations is not None else 10 * n
+    # Conjugate gradients converge in at most n steps in exact arithmetic; 2 n + 100 leaves room for rounding
+    # without turning a breakdown into millions of graph replays
+    limit = max_iterations if max_iterations is not None else 2 * n + 100
+    initial = float(torch.linalg.vector_norm(r)) / b_norm
+    if initial <= rtol or limit <= 0:  # e.g. a converged x0: nothing to iterate
+        return x, CgInfo(0, initial, initial <= rtol)
     tiny = torch.finfo(val.dtype).tiny
     spmv = getattr(ops, "csr_spmv_raw", None) if val.is_cuda else None
 
@@ -112,15 +117,17 @@ def cg(
         side = torch.cuda.Stream(device=val.device)
         side.wait_stream(torch.cuda.current_stream(val.device))
         with torch.cuda.stream(side):
-            for _ in range(3):  # warm-up outside capture (allocator, lazy module loading)
+            warm = min(3, limit)  # warm-up outside capture (allocator, lazy module loading); they are real iterations
+            for _ in range(warm):
                 iteration()
-            iterations = 3
+            iterations = warm
         torch.cuda.current_stream(val.device).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):  # records the launches, does not run them
             iteration()
         step = graph.replay
     rel = float("inf")
+    best, stalled = initial, 0
     while iterations < limit:
         step()
         iterations += 1
@@ -128,6 +135,17 @@ def cg(
             rel = float(torch.linalg.vector_norm(r)) / b_norm  # the only host synchronisation
             if rel <= rtol:
                 break
-    if rel == float("inf"):
+            # breakdown: a non-SPD or singular reduced system gives p.Ap <= 0 and then inf / NaN, or a residual
+            # that no longer decreases; stop and report instead of replaying to the iteration limit
+            if rel != rel or rel == float("inf"):
+                break
+            if rel < 0.999 * best:
+                best, stalled = rel, 0
+            else:
+                stalled += 1
+                if stalled >= 20:
+                    break
+    if rel == float("inf") and iterations > 0:
         rel = float(torch.linalg.vector_norm(r)) / b_norm
-    return x, CgInfo(iterations, rel, rel <= rtol)
+    converged = rel == rel and rel <= rtol
+    return x, CgInfo(iterations, rel, converged)

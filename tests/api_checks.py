@@ -190,8 +190,8 @@ def check_edges(mesh, g, device):
     basis = tfem.Basis(mesh, tfem.ElementTri(1, 2))
     u = torch.tensor(g[p + "interp_u"])
     val, grad = basis.interpolate(edges_basis, u)
-    close(val, g[p + "interp_edges"], rtol=1e-11, what="interp edges")
-    close(grad, g[p + "interp_edges_grad"], rtol=1e-11, what="interp edges grad")
+    close(val, g[p + "interp_edges"], rtol=1e-12, what="interp edges")
+    close(grad, g[p + "interp_edges_grad"], rtol=1e-12, what="interp edges grad")
     h_e = mesh["interior_edges", "length"].unsqueeze(-2)
     n_e = mesh["interior_edges", "normals"].unsqueeze(-2)
 
@@ -199,16 +199,16 @@ def check_edges(mesh, g, device):
         plus, minus = torch.unbind(grad, dim=-4)
         return size * ((plus * normal).sum(-1, keepdim=True) + (minus * -normal).sum(-1, keepdim=True)) ** 2
 
-    close(edges_basis.integrate_functional(jump, n_e, h_e), g[p + "eta"], rtol=1e-10, what="eta generic")
-    close(edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e), g[p + "eta"], rtol=1e-10, what="eta fused")
+    close(edges_basis.integrate_functional(jump, n_e, h_e), g[p + "eta"], rtol=1e-12, what="eta generic")
+    close(edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e), g[p + "eta"], rtol=1e-12, what="eta fused")
 
     interp, interp_grad = basis.interpolate(edges_basis)
 
     def nodal(nodes):
         return torch.sin(2.0 * nodes[..., [0]]) * torch.cos(nodes[..., [1]])
 
-    close(interp(nodal), g[p + "closure_edges"], rtol=1e-11, what="closure edges")
-    close(interp_grad(nodal), g[p + "closure_edges_grad"], rtol=1e-11, what="closure edges grad")
+    close(interp(nodal), g[p + "closure_edges"], rtol=1e-12, what="closure edges")
+    close(interp_grad(nodal), g[p + "closure_edges_grad"], rtol=1e-12, what="closure edges grad")
 
 
 def check_patches(g, device):
@@ -309,11 +309,11 @@ def check_fractures(g, device):
             basis = tfem.FractureBasis(mesh, tfem.ElementTri(1, 2))
             u = torch.tensor(g[p + "interp_u"])
             val, grad = basis.interpolate(edges_basis, u)
-            close(val, g[p + "interp_edges"], rtol=1e-11, what="frac interp edges")
-            close(grad, g[p + "interp_edges_grad"], rtol=1e-11, what="frac interp edges grad")
+            close(val, g[p + "interp_edges"], rtol=1e-12, what="frac interp edges")
+            close(grad, g[p + "interp_edges_grad"], rtol=1e-12, what="frac interp edges grad")
             h_e = mesh["interior_edges", "length"].unsqueeze(-2)
             n_e = mesh["interior_edges", "normals_3d"].unsqueeze(-2)
-            close(edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e), g[p + "eta"], rtol=1e-10, what="frac eta")
+            close(edges_basis.integrate_functional(forms.Jump(grad), n_e, h_e), g[p + "eta"], rtol=1e-12, what="frac eta")
         return aligned
 
 

@@ -81,6 +81,38 @@ def test_csr_diagonal_and_cg_small():
     assert np.abs(x.numpy() - ref).max() < 1e-10
 
 
+def test_cg_stops_on_breakdown_and_respects_limits():
+    """A non-SPD system must end with `converged == False` after a bounded number of iterations (not
+    10 n graph replays), a converged start vector needs no iteration, and tiny iteration limits are kept."""
+    n = 30
+    a = scipy.sparse.diags([np.r_[np.ones(n - 1), -1.0], 0.3 * np.ones(n - 1), 0.3 * np.ones(n - 1)], [0, 1, -1]).tocsr()
+    a.sort_indices()
+    crow, col = torch.from_numpy(a.indptr.astype(np.int32)), torch.from_numpy(a.indices.astype(np.int32))
+    val = torch.from_numpy(a.data)
+    b = torch.from_numpy(np.random.default_rng(1).standard_normal(n))
+    mp = pytest.MonkeyPatch()
+    try:
+        cpu_shim.install(mp)
+        singular = scipy.sparse.csr_matrix(np.zeros((n, n)) + np.diag(np.r_[np.ones(n - 1), 0.0]))
+        zero_row = (torch.from_numpy(singular.indptr.astype(np.int32)), torch.from_numpy(singular.indices.astype(np.int32)),
+                    torch.from_numpy(singular.data))
+        _, info = sparse.cg(*zero_row, torch.ones(n, dtype=torch.float64), rtol=1e-12, check_every=5)
+        assert not info.converged and info.iterations <= 2 * n + 100
+        _, info = sparse.cg(crow, col, val, b, rtol=1e-12, check_every=5)
+        assert info.iterations <= 2 * n + 100  # indefinite: either breaks down or happens to converge, never runs away
+        good = (a.T @ a + scipy.sparse.identity(n)).tocsr()
+        good.sort_indices()
+        g = (torch.from_numpy(good.indptr.astype(np.int32)), torch.from_numpy(good.indices.astype(np.int32)), torch.from_numpy(good.data))
+        x, info = sparse.cg(*g, b, rtol=1e-12, check_every=5)
+        assert info.converged
+        _, again = sparse.cg(*g, b, x0=x, rtol=1e-10)
+        assert again.converged and again.iterations == 0
+        _, short = sparse.cg(*g, b, rtol=1e-12, max_iterations=2)
+        assert short.iterations <= 2 and not short.converged
+    finally:
+        mp.undo()
+
+
 def test_solve_csr_path_host_logic(monkeypatch):
     cpu_shim.install(monkeypatch)
     check_solve("cpu", 24, 20, monkeypatch)
