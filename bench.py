@@ -49,6 +49,8 @@ def parse_args():
     p.add_argument("--ny", type=int, default=NY)
     p.add_argument("--path", default="tiled", choices=["tiled", "two_pass"])
     p.add_argument("--rows-per-tile", type=int, default=336)
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="multi-GPU runs: weak = one nx x ny strip PER GPU (default), strong = the ONE nx x ny mesh cut into N element ranges")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--permuted", action="store_true",
@@ -193,15 +195,21 @@ def run_reference(args):
 
 
 def workload_config(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = world > 1 and getattr(args, "scaling", "weak") == "strong"
+    per_gpu = 2 * args.nx * args.ny // world if strong else 2 * args.nx * args.ny
     return {
-        "workload": f"BASELINE config 2: structured unit-square P1 triangle mesh nx={args.nx} ny={args.ny} per GPU "
-        f"({2 * args.nx * args.ny} elements), interior vertices jittered U(-0.25h,0.25h) seed 1234, fp64, "
+        "workload": f"BASELINE config 2: structured unit-square P1 triangle mesh nx={args.nx} ny={args.ny} "
+        + (f"cut into {world} element ranges" if strong else "per GPU")
+        + f" ({2 * args.nx * args.ny} elements), interior vertices jittered U(-0.25h,0.25h) seed 1234, fp64, "
         "ElementTri(1,3) 4-point quadrature, grad u.grad v + u v to CSR values + load 2pi^2 sin(pi x) sin(pi y)",
-        "elements_per_gpu": 2 * args.nx * args.ny,
+        "elements_per_gpu": per_gpu,
         "path": args.path,
         "l2": "flushed between timed steps (256 MiB write)",
         "symbolic": "CSR pattern + tile plan built once, outside the timed region",
-        "multi_gpu": "weak scaling: one strip of the same size per GPU; interface rows are packed straight into the owner's "
+        "multi_gpu": ("strong scaling: the one mesh is cut into contiguous element ranges, one per GPU; " if strong else
+                      "weak scaling: one strip of the same size per GPU; ")
+        + "interface rows are packed straight into the owner's "
         "receive buffer over NVLink peer memory (signal-pad handshake; TFEM_EXCHANGE=nccl selects one all_gather instead) "
         "and added by their owners on a side stream while the interior tiles assemble",
     }
@@ -235,7 +243,13 @@ def run_ours(args):
     else:
         from pytorch_fem_solver_b200 import distributed
 
-        assembler = distributed.StripAssembly(args.nx, args.ny, rank, world, device, QUAD_ORDER, rows_per_tile=args.rows_per_tile)
+        if args.scaling == "strong":
+            global_mesh = tfem.meshgen.structured_rectangle(args.nx, args.ny, jitter=0.25, seed=1234, topology=False)
+            assembler = distributed.PartitionedAssembly.from_mesh(global_mesh, rank, world, device, quad_order=QUAD_ORDER,
+                                                                  rows_per_tile=args.rows_per_tile)
+            del global_mesh
+        else:
+            assembler = distributed.StripAssembly(args.nx, args.ny, rank, world, device, QUAD_ORDER, rows_per_tile=args.rows_per_tile)
         basis = assembler.basis
         mesh_dict = assembler.mesh_dict
 
@@ -272,9 +286,11 @@ def run_ours(args):
 
     if assembler is not None and args.path == "tiled":
         # interface tiles first, then interior tiles while the NCCL exchange runs on a side stream
-        step = assembler.step
+        # the whole step (assembly launch + side-stream exchange) replayed from CUDA graphs where it can be captured
+        captured = assembler.capture()
+        step = assembler.replay if captured else assembler.step
         kernels_per_step = 2 + assembler.fused_exchange.n_kernels
-        exchange_kind = type(assembler.fused_exchange).__name__
+        exchange_kind = type(assembler.fused_exchange).__name__ + (" (step replayed from CUDA graphs)" if captured else "")
     elif assembler is not None:
 
         def step():
@@ -382,7 +398,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     total_ms, kernel_ms, e2e_step_s = stats.tolist()
-    total_elements = n_el * world
+    strong = world > 1 and args.scaling == "strong"
+    total_elements = 2 * args.nx * args.ny if strong else n_el * world
 
     if rank == 0:
         peak, peak_source = measured_peak()
@@ -397,7 +414,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",

@@ -344,32 +344,39 @@ class PeerExchange:
         self.steps += 1
 
 
-class StripAssembly:
-    """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip.
+class PartitionedAssembly:
+    """Element-partitioned assembly of ANY planar P1 triangle mesh: this rank holds a slice of the global
+    element list (`conn_global`, global vertex ids), assembles it with the single-GPU kernels into a local
+    CSR system and exchanges the interface rows with their owners.
 
     `step()` is one persistent launch that walks the tiles holding interface rows first; the interface
     exchange (pack into the owner's peer buffer -> signal -> add) runs on a side stream while the same
     launch continues with the interior tiles.  With the collective transport (`TFEM_EXCHANGE=nccl`, gloo
-    tests) the interface and interior tiles are two launches and the exchange sits between them."""
+    tests) the interface and interior tiles are two launches and the exchange sits between them.
 
-    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=336, group=None, exchange_ops=None):
+    `vertices` is the global (n_global, 2) coordinate array or a callable `ids -> (len(ids), 2)`; only the
+    vertices this rank's elements touch are ever looked at (ghost columns carry no geometry)."""
+
+    def __init__(self, vertices, conn_global, n_global, rank, world, device, quad_order=3, rows_per_tile=336, group=None,
+                 exchange_ops=None, markers=None):
         import numpy as np
 
         from . import ElementTri, MeshTri, forms
 
-        mesh, offset, n_global = strip_mesh(nx, ny, rank, world)
-        conn_global = torch.from_numpy(mesh["triangles"].astype(np.int64) + offset).to(device)
+        conn_global = torch.as_tensor(conn_global).to(device=device, dtype=torch.int64)
         self.plan = InterfacePlan(conn_global, n_global, rank, world, group)
-        if self.plan.n_ghost:
-            pad = np.zeros((self.plan.n_ghost, 2))
-            mesh["vertices"] = np.concatenate([mesh["vertices"], pad])
-            mesh["vertex_markers"] = np.concatenate([mesh["vertex_markers"], np.zeros((self.plan.n_ghost, 1), dtype=np.int32)])
-        self.mesh_dict = mesh
+        local_ids = self.plan.local_to_global.cpu().numpy()
+        touched = np.zeros(local_ids.shape[0], dtype=bool)
+        touched[np.unique(self.plan.dof_conn.cpu().numpy())] = True
+        coords = np.zeros((local_ids.shape[0], 2))
+        coords[touched] = vertices(local_ids[touched]) if callable(vertices) else np.asarray(vertices)[local_ids[touched]]
+        vertex_markers = np.zeros((local_ids.shape[0], 1), dtype=np.int32)
+        if markers is not None:
+            vertex_markers[touched] = np.asarray(markers).reshape(-1, 1)[local_ids[touched]]
+        self.mesh_dict = {"vertices": coords, "triangles": self.plan.dof_conn.cpu().numpy().astype(np.int32), "vertex_markers": vertex_markers}
+        self.local_to_global = self.plan.local_to_global
         with torch.device(device):
-            self.basis = _basis_for(MeshTri(mesh), ElementTri(1, quad_order))
-        # strips are contiguous ranges of global ids, so local ids are global ids minus a constant
-        # and ghosts (the vertex row above the strip) sort to the end: local numbering is unchanged
-        assert torch.equal(self.plan.dof_conn.cpu(), torch.from_numpy(mesh["triangles"]).to(torch.int32))
+            self.basis = _basis_for(MeshTri(self.mesh_dict), ElementTri(1, quad_order))
         self.basis._pattern = csr_mod.build_pattern(self.basis._dof_conn_flat(), self.plan.n_local, self.plan.extra_keys)
         self.plan.bind(self.basis.pattern)
         self.exchange = InterfaceExchange(self.plan, exchange_ops)
@@ -384,10 +391,12 @@ class StripAssembly:
         interface_local = torch.searchsorted(self.plan.local_to_global, self.plan.interface_global)
         is_interface_tile = torch.zeros(full.n_tiles, dtype=torch.bool, device=device)
         is_interface_tile[full.tile_of_row[interface_local]] = True
-        self.interface_tiles = full.subset(torch.nonzero(is_interface_tile, as_tuple=True)[0])
+        # inside each group keep the plan's own order (congruent tiles adjacent: a CTA rarely changes template)
+        order = full.default_order.long()
+        self.interface_tiles = full.subset(order[is_interface_tile[order]])
         # the interior launch leaves some CTA slots free so the exchange kernels can run beside it
         reserve = int(os.environ.get("TFEM_RESERVE_CTAS", "8"))
-        self.interior_tiles = full.subset(torch.nonzero(~is_interface_tile, as_tuple=True)[0], reserve_ctas=reserve)
+        self.interior_tiles = full.subset(order[~is_interface_tile[order]], reserve_ctas=reserve)
         self.full_plan = full
         # one launch, interface tiles first, counted on a device counter the pack kernels wait for
         self.progress = torch.zeros(1, dtype=torch.int32, device=device)
@@ -404,6 +413,17 @@ class StripAssembly:
             self._previous_step.record(torch.cuda.current_stream())
         # ranks leave set-up together: the first step's device-side waits (bounded) then only see kernel-scale skew
         dist.barrier(group=self.plan.group)
+
+    @classmethod
+    def from_mesh(cls, mesh_dict, rank, world, device, **kwargs):
+        """Strong scaling: rank `rank` takes the `rank`-th of `world` contiguous ranges of the mesh's element list."""
+        import numpy as np
+
+        triangles = np.asarray(mesh_dict["triangles"])
+        n_el = triangles.shape[0]
+        lo, hi = (n_el * rank) // world, (n_el * (rank + 1)) // world
+        return cls(np.asarray(mesh_dict["vertices"]), triangles[lo:hi].astype(np.int64), int(np.asarray(mesh_dict["vertices"]).shape[0]),
+                   rank, world, device, markers=mesh_dict.get("vertex_markers"), **kwargs)
 
     def _make_exchange(self, nnz, device, exchange_ops):
         """Peer-memory stores + signals on NVLink when the ranks are CUDA peers (TFEM_EXCHANGE=peer, the
@@ -426,6 +446,75 @@ class StripAssembly:
         ops.assemble_csr_tiled(plan.c_struct(), self.basis._layout.coords if coords is None else coords, self.quad_order,
                                alpha, beta, self.source.kind, self.source.params, buffer[:nnz], buffer[nnz:])
 
+    def _single_launch_step(self, main, alpha, beta, coords, buffer, captured: bool):
+        """ONE persistent launch walks the interface tiles first and counts them on a device counter; the pack
+        kernels on the side stream wait for that counter, store over NVLink into the owners' buffers and signal,
+        while the same launch goes on with the interior tiles.  `captured`: the call is being recorded into a CUDA
+        graph."""
+        # the counter restarts every step (the previous step's waiters are done: the calling stream has waited for
+        # them), so eager steps and graph replays can be mixed and every replay waits for the same target
+        target = self.n_interface_tiles * self.ordered_tiles.consumer_warps
+        self.progress.zero_()
+        # everything the calling stream has waited for so far (the previous step, and in the host pipeline
+        # the copies that free `coords` / `buffer`) also gates the side stream
+        entered = torch.cuda.Event()
+        entered.record(main)
+        self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
+        with torch.cuda.stream(self.side_stream):
+            if not captured:
+                self.side_stream.wait_event(self._previous_step)  # the buffer's previous contents are final
+            self.side_stream.wait_event(entered)
+            self.fused_exchange.pack(buffer, self.progress, target)
+            self.fused_exchange.wait_local(buffer, self.progress, target)
+            self.fused_exchange.gather_add(buffer)
+            finished = torch.cuda.Event()
+            finished.record(self.side_stream)
+        main.wait_event(finished)
+        if not captured:
+            self._previous_step.record(main)
+
+    def capture(self, alpha: float = 1.0, beta: float = 1.0) -> bool:
+        """Record `step()` (assembly launch + side-stream exchange with its NVLink signals) into two CUDA graphs, one
+        per receive-buffer half; `replay()` then costs one graph launch on the host instead of ~15 enqueues, which
+        is what bounds a step once the per-rank work drops below ~90 us (strong scaling).  Returns False (and
+        leaves `replay` = `step`) where the step cannot be captured."""
+        self._graphs = None
+        if not self.single_launch or self.side_stream is None or os.environ.get("TFEM_STEP_GRAPH", "1") != "1":
+            return False
+        exchange = self.fused_exchange
+        while exchange.steps < 2 or exchange.steps & 1:  # past the start-up steps, next step on half 0
+            self.step(alpha, beta)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.plan.group)
+        stream = torch.cuda.Stream(device=self.buffer.device)
+        graphs = []
+        try:
+            for parity in (0, 1):
+                assert exchange.steps & 1 == parity
+                graph = torch.cuda.CUDAGraph()
+                stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                    self._single_launch_step(torch.cuda.current_stream(), alpha, beta, None, self.buffer, captured=True)
+                graphs.append(graph)
+                graph.replay()  # the recorded step has not run yet: run it, every rank the same parity
+                torch.cuda.synchronize()
+        except Exception as error:  # noqa: BLE001 - reported; the eager step keeps working
+            import sys
+
+            print(f"[tfem] step graph capture unavailable ({error!r}); using eager launches", file=sys.stderr)
+            return False
+        self._graphs = graphs
+        self._graph_parity = exchange.steps & 1
+        return True
+
+    def replay(self):
+        """One distributed assembly through the captured graphs (after `capture()`), else a plain `step()`."""
+        if getattr(self, "_graphs", None) is None:
+            return self.step()
+        self._graphs[self._graph_parity].replay()
+        self._graph_parity ^= 1
+        self.fused_exchange.steps += 1
+
     def step(self, alpha: float = 1.0, beta: float = 1.0, coords: Optional[torch.Tensor] = None,
              buffer: Optional[torch.Tensor] = None):
         """One distributed assembly (owned rows complete) into `self.values` / `self.load`, or into
@@ -436,25 +525,7 @@ class StripAssembly:
             self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
             return
         if self.single_launch:
-            # ONE persistent launch walks the interface tiles first and counts them on a device
-            # counter; the pack kernels on the side stream wait for that counter, store over NVLink
-            # into the owners' buffers and signal, while the same launch goes on with the interior
-            self.progress_target += self.n_interface_tiles * self.ordered_tiles.consumer_warps
-            # everything the calling stream has waited for so far (the previous step, and in the host pipeline
-            # the copies that free `coords` / `buffer`) also gates the side stream
-            entered = torch.cuda.Event()
-            entered.record(main)
-            self._launch(self.ordered_tiles, alpha, beta, coords, buffer)
-            with torch.cuda.stream(self.side_stream):
-                self.side_stream.wait_event(self._previous_step)  # the buffer's previous contents are final
-                self.side_stream.wait_event(entered)
-                self.fused_exchange.pack(buffer, self.progress, self.progress_target)
-                self.fused_exchange.wait_local(buffer, self.progress, self.progress_target)
-                self.fused_exchange.gather_add(buffer)
-                finished = torch.cuda.Event()
-                finished.record(self.side_stream)
-            main.wait_event(finished)
-            self._previous_step.record(main)
+            self._single_launch_step(main, alpha, beta, coords, buffer, captured=False)
             return
         self._launch(self.interface_tiles, alpha, beta, coords, buffer)
         ready = torch.cuda.Event()
@@ -470,12 +541,31 @@ class StripAssembly:
         main.wait_event(finished)
 
 
+class StripAssembly(PartitionedAssembly):
+    """Weak-scaling driver of bench.py: every rank owns a 2*nx*ny-element strip of a mesh `world` times taller."""
+
+    def __init__(self, nx, ny, rank, world, device, quad_order=3, rows_per_tile=336, group=None, exchange_ops=None):
+        import numpy as np
+
+        mesh, offset, n_global = strip_mesh(nx, ny, rank, world)
+        strip_vertices = mesh["vertices"]
+
+        def vertices(ids):  # global ids of this strip are local ids plus a constant
+            return strip_vertices[ids - offset]
+
+        super().__init__(vertices, mesh["triangles"].astype(np.int64) + offset, n_global, rank, world, device, quad_order, rows_per_tile,
+                         group, exchange_ops)
+        # strips are contiguous ranges of global ids, so local ids are global ids minus a constant
+        # and ghosts (the vertex row above the strip) sort to the end: local numbering is unchanged
+        assert torch.equal(self.plan.dof_conn.cpu(), torch.from_numpy(mesh["triangles"]).to(torch.int32))
+
+
 class StripHostPipeline:
     """`StripAssembly.step` fed from / drained to pinned HOST memory with `depth` steps in flight: the
     host->device copy of step i+1, the distributed assembly of step i (launch + interface exchange) and
     the device->host copy of step i-1 overlap on three streams (see basis.HostPipeline for one GPU)."""
 
-    def __init__(self, assembler: StripAssembly, depth: int = 2):
+    def __init__(self, assembler: PartitionedAssembly, depth: int = 2):
         self.assembler, self.depth = assembler, max(int(depth), 1)
         coords = assembler.basis._layout.coords
         self.coords = [torch.empty_like(coords) for _ in range(self.depth)]

@@ -186,7 +186,8 @@ def detect_lattice(pattern: CsrPattern):
         if width < 2 or n % width != 0:
             continue
         last_in_row = (torch.arange(n, device=crow.device) % width) == width - 1
-        if not bool((has_next & last_in_row).any()) and bool(has_next[~last_in_row].all()):
+        populated = length > 0  # rows without entries (ghost columns of a multi-GPU owner) say nothing
+        if not bool((has_next & last_in_row).any()) and bool(has_next[~last_in_row & populated].all()):
             return int(width)
     return 0
 
@@ -475,8 +476,8 @@ def _build_tile_plan(
     arange = lambda n: torch.arange(n, device=device)  # noqa: E731
 
     # 1. rows -> tiles.  Only rows some element touches are clustered; rows without elements
-    #    (isolated vertices, ghost columns of a multi-GPU owner) carry no work and are dealt out
-    #    evenly afterwards so that their (zero) load entry is still written.
+    #    (isolated vertices, ghost columns of a multi-GPU owner) carry no work and are put into
+    #    tiles of their own afterwards so that their (zero) load entry is still written.
     active = torch.zeros(n_dof, dtype=torch.bool, device=device)
     active[dconn.reshape(-1)] = True
     active_rows = torch.nonzero(active, as_tuple=True)[0]
@@ -510,8 +511,14 @@ def _build_tile_plan(
         n_tiles = max((n_active + rows_per_tile - 1) // rows_per_tile, 1)
     tile_of_row = torch.empty(n_dof, dtype=torch.int64, device=device)
     tile_of_row[active_rows] = tile_of_active
+    # rows without elements get tiles of their own (no elements, only rows): dealing them out over the
+    # other tiles would make otherwise congruent tiles differ and defeat the template sharing
     idle_rows = torch.nonzero(~active, as_tuple=True)[0]
-    tile_of_row[idle_rows] = arange(idle_rows.numel()) % n_tiles
+    if idle_rows.numel():
+        if n_active == 0:
+            n_tiles = 0
+        tile_of_row[idle_rows] = n_tiles + torch.div(arange(idle_rows.numel()), rows_per_tile, rounding_mode="floor")
+        n_tiles += (int(idle_rows.numel()) + rows_per_tile - 1) // rows_per_tile
     tiles = arange(n_tiles)
 
     # 2. (tile, element) incidences, tile-major / element ascending
