@@ -210,6 +210,16 @@ int tfem_sm_count(void);
                                    int quad_order, const T* frac_jac, const T* frac_inv,           \
                                    const T* frac_det, const T* r_bar, T* grad_u_bar,               \
                                    void* stream);                                                  \
+  /* The same residual for a BATCH OF SMALL MESHES whose DOFs are private to each mesh           \
+   * (PatchesBasis, basis/patches_basis.py:44-105; examples/example_patches.py:102-113), summed   \
+   * to r [n_mesh, n_vert_per_mesh] in ONE launch: a lane group per mesh, a lane per element,     \
+   * DOF sums by warp shuffles in increasing element order.  n_el_per_mesh <= 8,                  \
+   * n_vert_per_mesh <= 16, planar (d = 2); grad_u [n_mesh * n_el_per_mesh, n_q, 2].  Its adjoint \
+   * is tfem_weak_residual_bwd with dof_conn[e][k] = mesh * n_vert_per_mesh + conn[e][k]. */      \
+  int tfem_batched_weak_residual_##SUF(int64_t n_mesh, int n_el_per_mesh, int n_vert_per_mesh,     \
+                                       const T* coords, const int32_t* conn, int quad_order,       \
+                                       const tfem_source* host_source, const T* f_q,               \
+                                       const T* grad_u, T* r, void* stream);                       \
   /* Basis.interpolate(self, u) (basis/basis.py:105-112,149-159; fracture_basis.py:214-223):     \
    * val[e,q] = sum_i u[dof_conn[e,i]] phi_i(q),  grad[e,:] = sum_i u[...] grad phi_i[e,:]. */    \
   int tfem_interp_cells_##SUF(int64_t n_el, const int32_t* dof_conn, const T* v_grad, int d,       \

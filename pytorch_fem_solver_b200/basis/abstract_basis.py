@@ -59,6 +59,7 @@ class AbstractBasis(abc.ABC):
         self._element = element
         self.mesh = ops.place_mesh(mesh)
         self._geometry = None
+        self._geometry_version = 0
         self._pattern = None
         self._scatter_inverse = {}
         self._tile_plans = {}
@@ -167,6 +168,24 @@ class AbstractBasis(abc.ABC):
             self._tile_plans[key] = csr_mod.build_tile_plan(geom_conn, dof_conn, self.pattern, points, rows_per_tile, ordering)
         return self._tile_plans[key]
 
+    def _sampled_source(self, src) -> torch.Tensor:
+        """f at this basis' quadrature points, (N_total, n_q).  The points of a basis are fixed, so the samples of
+        a `forms.SampledSource` are evaluated once per (source object, basis, geometry) and reused by every later
+        call -- a training loop calls the residual thousands of times with the same right-hand side
+        (examples/example_weak.py:64-75).  `source.refresh()` drops them (a callable with changing state)."""
+        lay = self._layout
+        key = (id(self), self._geometry_version, self.dtype)
+        cache = getattr(src, "_samples", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                values = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+            cache = (key, values)
+            try:
+                src._samples = cache
+            except AttributeError:  # a source type without attribute storage: evaluate every time
+                pass
+        return cache[1]
+
     # ------------------------------------------------------------------ integrate_*
     def _reduce_integrand(self, integrand: torch.Tensor) -> torch.Tensor:
         """`(f * dx).sum(-3)` -> (N_total, a*b) for an integrand broadcastable to (*lead, q, a, b)."""
@@ -214,9 +233,7 @@ class AbstractBasis(abc.ABC):
         if isinstance(function, forms.WeakResidual) and len(args) == 1 and not kwargs:
             src = function.source
             grad = forms.WeakResidual.field(self, args[0])
-            f_q = None
-            if src.kind == ops.SRC_SAMPLED:
-                f_q = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+            f_q = self._sampled_source(src) if src.kind == ops.SRC_SAMPLED else None
             vec = ops.weak_residual(
                 grad.to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous(), lay.coords, lay.conn,
                 self._dof_conn_flat(), pat.lin_seg, pat.lin_perm, lay.n_el_per_mesh, lay.n_vert_per_mesh,
@@ -252,6 +269,7 @@ class AbstractBasis(abc.ABC):
         lay = self._layout
         lay.coords.copy_(coords_host.reshape(lay.coords.shape), non_blocking=True)
         self._geometry = None  # cached v_grad / points / dx belong to the old coordinates
+        self._geometry_version += 1
         values, vec = self._assemble_fused(bilinear, load.source if load is not None else None, path)
         hook = getattr(self, "_post_assemble_hook", None)
         if hook is not None:
@@ -286,9 +304,7 @@ class AbstractBasis(abc.ABC):
             ops.assemble_csr_tiled(plan.c_struct(), lay.coords, order, alpha, beta, src.kind if want_vec else 0,
                                    src.params, values, vec)
             return values, vec
-        f_q = None
-        if want_vec and src.kind == ops.SRC_SAMPLED:
-            f_q = src(self.integration_points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+        f_q = self._sampled_source(src) if want_vec and src.kind == ops.SRC_SAMPLED else None
         local_mat, local_vec = ops.local_forms(
             lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh, order, alpha, beta, want_mat,
             src.kind if want_vec else 0, list(src.params), f_q, *lay.frac_args(),

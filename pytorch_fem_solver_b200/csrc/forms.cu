@@ -128,14 +128,33 @@ __global__ void __launch_bounds__(256) local_forms_kernel(
 // (examples/example_weak.py:64-75 integrated by abstract_basis.py:95-104).  grad_u is the big
 // stream (n_q * d values per element) and is read exactly once.
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool FRAC>
+// The grad_u (and sampled f) rows of a block's 256 elements are copied to shared memory with fully
+// coalesced loads (consecutive lanes, consecutive addresses) and read back row by row from a padded,
+// bank-conflict-free layout: the per-element stride in global memory (144 B for the 6-point rule on a
+// fracture) would otherwise make every warp load touch 32 different lines.
+template <typename T, bool FRAC, int NQ>
 __global__ void __launch_bounds__(256) weak_residual_local_kernel(
     int n_el, int n_el_per_mesh, int n_vert_per_mesh, const T* __restrict__ coords,
     const int32_t* __restrict__ conn, const QuadT<T> quad, const FracLite<T> frac,
     const SourceT<T> src, const T* __restrict__ f_q, const T* __restrict__ grad_u,
     T* __restrict__ local_vec) {
   constexpr int D = FRAC ? 3 : 2;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int ROW = NQ * D, ROWP = ROW | 1;  // odd stride: conflict-free rows
+  constexpr int FROWP = NQ | 1;
+  __shared__ T s_gu[256 * ROWP];
+  __shared__ T s_f[256 * FROWP];
+  const int e0 = blockIdx.x * 256;
+  const int count = min(256, n_el - e0);
+  {
+    const T* g = grad_u + (int64_t)e0 * ROW;
+    for (int i = threadIdx.x; i < count * ROW; i += 256) s_gu[(i / ROW) * ROWP + i % ROW] = __ldg(g + i);
+    if (src.kind == TFEM_SRC_SAMPLED) {
+      const T* f = f_q + (int64_t)e0 * NQ;
+      for (int i = threadIdx.x; i < count * NQ; i += 256) s_f[(i / NQ) * FROWP + i % NQ] = __ldg(f + i);
+    }
+  }
+  __syncthreads();
+  const int e = e0 + threadIdx.x;
   if (e >= n_el) return;
   const int mesh = e / n_el_per_mesh;
   const int64_t voff = (int64_t)mesh * n_vert_per_mesh;
@@ -177,11 +196,12 @@ __global__ void __launch_bounds__(256) weak_residual_local_kernel(
   }
   const T det = g.det * detf;
   T r0 = T(0), r1 = T(0), r2 = T(0);
-  const T* gu = grad_u + (int64_t)e * quad.n_q * D;
-  for (int q = 0; q < quad.n_q; ++q) {
+  const T* gu = s_gu + threadIdx.x * ROWP;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
     T f = T(0);
     if (src.kind == TFEM_SRC_SAMPLED) {
-      f = __ldg(f_q + (int64_t)e * quad.n_q + q);
+      f = s_f[threadIdx.x * FROWP + q];
     } else if (src.kind != TFEM_SRC_NONE) {
       T px = quad.l0[q] * x0 + quad.l1[q] * x1 + quad.l2[q] * x2;
       T py = quad.l0[q] * y0 + quad.l1[q] * y1 + quad.l2[q] * y2;
@@ -194,9 +214,9 @@ __global__ void __launch_bounds__(256) weak_residual_local_kernel(
       f = source_eval(src, px, py);
     }
     T u[3];
-    u[0] = __ldg(gu + q * D);
-    u[1] = __ldg(gu + q * D + 1);
-    u[2] = D == 3 ? __ldg(gu + q * D + (D - 1)) : T(0);
+    u[0] = gu[q * D];
+    u[1] = gu[q * D + 1];
+    u[2] = D == 3 ? gu[q * D + (D - 1)] : T(0);
     const T dxq = quad.w[q] * det;
     T d0 = gr[0][0] * u[0] + gr[0][1] * u[1];
     T d1 = gr[1][0] * u[0] + gr[1][1] * u[1];
@@ -216,46 +236,134 @@ __global__ void __launch_bounds__(256) weak_residual_local_kernel(
   out[2] = r2;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weak residual of a BATCH OF SMALL MESHES whose DOFs are private to each mesh (PatchesBasis:
+// 4 triangles around a centre vertex, 5 DOFs; examples/example_patches.py:102-113), in ONE launch:
+// a group of G lanes takes one mesh, lane t integrates element t, and the (at most 8) DOF sums of
+// the mesh are formed with warp shuffles in increasing element order -- the order of the reference's
+// index_put_ -- and written straight to r[mesh, dof].  No per-element array, no scatter launch.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(256) batched_weak_residual_kernel(
+    int n_mesh, int n_el_per_mesh, int n_vert_per_mesh, const T* __restrict__ coords,
+    const int32_t* __restrict__ conn, const QuadT<T> quad, const SourceT<T> src,
+    const T* __restrict__ f_q, const T* __restrict__ grad_u, T* __restrict__ r) {
+  const int thread = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mesh = thread / G, t = thread % G;
+  const bool active = mesh < n_mesh && t < n_el_per_mesh;
+  int v0 = -1, v1 = -1, v2 = -1;
+  T r0 = T(0), r1 = T(0), r2 = T(0);
+  if (active) {
+    const int64_t e = (int64_t)mesh * n_el_per_mesh + t;
+    const int64_t voff = (int64_t)mesh * n_vert_per_mesh;
+    v0 = __ldg(conn + 3 * e + 0);
+    v1 = __ldg(conn + 3 * e + 1);
+    v2 = __ldg(conn + 3 * e + 2);
+    T x0, y0, x1, y1, x2, y2;
+    load_xy(coords, voff + v0, x0, y0);
+    load_xy(coords, voff + v1, x1, y1);
+    load_xy(coords, voff + v2, x2, y2);
+    const TriGeom<T> g = tri_geom(x0, y0, x1, y1, x2, y2);
+    const T g00 = -g.i00 - g.i10, g01 = -g.i01 - g.i11;
+    const T* gu = grad_u + e * quad.n_q * 2;
+    for (int q = 0; q < quad.n_q; ++q) {
+      T f = T(0);
+      if (src.kind == TFEM_SRC_SAMPLED) {
+        f = __ldg(f_q + e * quad.n_q + q);
+      } else if (src.kind != TFEM_SRC_NONE) {
+        const T px = quad.l0[q] * x0 + quad.l1[q] * x1 + quad.l2[q] * x2;
+        const T py = quad.l0[q] * y0 + quad.l1[q] * y1 + quad.l2[q] * y2;
+        f = source_eval(src, px, py);
+      }
+      const T ux = __ldg(gu + 2 * q), uy = __ldg(gu + 2 * q + 1);
+      const T dxq = quad.w[q] * g.det;
+      r0 += dxq * (f * quad.l0[q] - (g00 * ux + g01 * uy));
+      r1 += dxq * (f * quad.l1[q] - (g.i00 * ux + g.i01 * uy));
+      r2 += dxq * (f * quad.l2[q] - (g.i10 * ux + g.i11 * uy));
+    }
+  }
+  const unsigned base = (threadIdx.x & 31u) - (unsigned)t;  // first lane of this group
+  for (int v = 0; v < n_vert_per_mesh; ++v) {
+    const T mine = (v0 == v ? r0 : T(0)) + (v1 == v ? r1 : T(0)) + (v2 == v ? r2 : T(0));
+    T sum = __shfl_sync(0xffffffffu, mine, base);
+    for (int k = 1; k < n_el_per_mesh; ++k) sum += __shfl_sync(0xffffffffu, mine, base + k);
+    if (mesh < n_mesh && t == v % G) r[(int64_t)mesh * n_vert_per_mesh + v] = sum;
+  }
+}
+
+template <typename T>
+int batched_weak_residual(int64_t n_mesh, int n_el_per_mesh, int n_vert_per_mesh, const T* coords, const int32_t* conn,
+                          int quad_order, const tfem_source* source, const T* f_q, const T* grad_u, T* r, void* stream) {
+  if (n_mesh < 0 || n_el_per_mesh <= 0 || n_el_per_mesh > 8 || n_vert_per_mesh <= 0 || n_vert_per_mesh > 16) return TFEM_ERR_BAD_ARG;
+  if (n_mesh == 0) return TFEM_OK;
+  if (!coords || !conn || !grad_u || !r) return TFEM_ERR_BAD_ARG;
+  if (n_mesh * 8 > kMaxIndex) return TFEM_ERR_TOO_LARGE;
+  if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
+  const SourceT<T> src = make_source<T>(source);
+  if (src.kind < TFEM_SRC_NONE || src.kind > TFEM_SRC_SINSIN) return TFEM_ERR_BAD_ARG;
+  if (src.kind == TFEM_SRC_SAMPLED && !f_q) return TFEM_ERR_BAD_ARG;
+  const QuadT<T> quad = make_quad<T>(quad_order);
+  auto s = static_cast<cudaStream_t>(stream);
+  if (n_el_per_mesh <= 4)
+    batched_weak_residual_kernel<T, 4><<<blocks_for(n_mesh * 4, 256), 256, 0, s>>>((int)n_mesh, n_el_per_mesh, n_vert_per_mesh, coords, conn, quad,
+                                                                                  src, f_q, grad_u, r);
+  else
+    batched_weak_residual_kernel<T, 8><<<blocks_for(n_mesh * 8, 256), 256, 0, s>>>((int)n_mesh, n_el_per_mesh, n_vert_per_mesh, coords, conn, quad,
+                                                                                  src, f_q, grad_u, r);
+  return check_launch();
+}
+
 // grad_u_bar[e,q,:] = -dx[e,q] * sum_i grad phi_i[e,:] * r_bar[dof_conn[e,i]]
-template <typename T, bool FRAC>
+// Each thread lays its element's n_q * d values out in a padded shared-memory row; the block then writes
+// the 256 rows with fully coalesced stores.
+template <typename T, bool FRAC, int NQ>
 __global__ void __launch_bounds__(256) weak_residual_bwd_kernel(
     int n_el, int n_el_per_mesh, int n_vert_per_mesh, const T* __restrict__ coords,
     const int32_t* __restrict__ conn, const int32_t* __restrict__ dof_conn, const QuadT<T> quad,
     const FracLite<T> frac, const T* __restrict__ r_bar, T* __restrict__ grad_u_bar) {
   constexpr int D = FRAC ? 3 : 2;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_el) return;
-  const int mesh = e / n_el_per_mesh;
-  const int64_t voff = (int64_t)mesh * n_vert_per_mesh;
-  const int v0 = __ldg(conn + 3 * (int64_t)e + 0);
-  const int v1 = __ldg(conn + 3 * (int64_t)e + 1);
-  const int v2 = __ldg(conn + 3 * (int64_t)e + 2);
-  T x0, y0, x1, y1, x2, y2;
-  load_xy(coords, voff + v0, x0, y0);
-  load_xy(coords, voff + v1, x1, y1);
-  load_xy(coords, voff + v2, x2, y2);
-  const TriGeom<T> g = tri_geom(x0, y0, x1, y1, x2, y2);
-  const T rb0 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 0));
-  const T rb1 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 1));
-  const T rb2 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 2));
-  // s = sum_i r_bar_i grad phi_i (2-D), then mapped to 3-D with J_f^+ for fractures
-  const T s0 = rb0 * (-g.i00 - g.i10) + rb1 * g.i00 + rb2 * g.i10;
-  const T s1 = rb0 * (-g.i01 - g.i11) + rb1 * g.i01 + rb2 * g.i11;
-  T s[3] = {s0, s1, T(0)};
-  T detf = T(1);
-  if constexpr (FRAC) {
-    detf = __ldg(frac.det + mesh);
+  constexpr int ROW = NQ * D, ROWP = ROW | 1;
+  __shared__ T s_out[256 * ROWP];
+  const int e0 = blockIdx.x * 256;
+  const int count = min(256, n_el - e0);
+  const int e = e0 + threadIdx.x;
+  if (e < n_el) {
+    const int mesh = e / n_el_per_mesh;
+    const int64_t voff = (int64_t)mesh * n_vert_per_mesh;
+    const int v0 = __ldg(conn + 3 * (int64_t)e + 0);
+    const int v1 = __ldg(conn + 3 * (int64_t)e + 1);
+    const int v2 = __ldg(conn + 3 * (int64_t)e + 2);
+    T x0, y0, x1, y1, x2, y2;
+    load_xy(coords, voff + v0, x0, y0);
+    load_xy(coords, voff + v1, x1, y1);
+    load_xy(coords, voff + v2, x2, y2);
+    const TriGeom<T> g = tri_geom(x0, y0, x1, y1, x2, y2);
+    const T rb0 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 0));
+    const T rb1 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 1));
+    const T rb2 = __ldg(r_bar + __ldg(dof_conn + 3 * (int64_t)e + 2));
+    // s = sum_i r_bar_i grad phi_i (2-D), then mapped to 3-D with J_f^+ for fractures
+    const T s0 = rb0 * (-g.i00 - g.i10) + rb1 * g.i00 + rb2 * g.i10;
+    const T s1 = rb0 * (-g.i01 - g.i11) + rb1 * g.i01 + rb2 * g.i11;
+    T sv[3] = {s0, s1, T(0)};
+    T detf = T(1);
+    if constexpr (FRAC) {
+      detf = __ldg(frac.det + mesh);
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-      s[c] = s0 * __ldg(frac.inv + 6 * mesh + c) + s1 * __ldg(frac.inv + 6 * mesh + 3 + c);
-  }
-  const T det = g.det * detf;
-  T* out = grad_u_bar + (int64_t)e * quad.n_q * D;
-  for (int q = 0; q < quad.n_q; ++q) {
-    const T dxq = -(quad.w[q] * det);
+      for (int c = 0; c < 3; ++c)
+        sv[c] = s0 * __ldg(frac.inv + 6 * mesh + c) + s1 * __ldg(frac.inv + 6 * mesh + 3 + c);
+    }
+    const T det = g.det * detf;
+    T* row = s_out + threadIdx.x * ROWP;
 #pragma unroll
-    for (int c = 0; c < D; ++c) out[q * D + c] = dxq * s[c];
+    for (int q = 0; q < NQ; ++q) {
+      const T dxq = -(quad.w[q] * det);
+#pragma unroll
+      for (int c = 0; c < D; ++c) row[q * D + c] = dxq * sv[c];
+    }
   }
+  __syncthreads();
+  T* out = grad_u_bar + (int64_t)e0 * ROW;
+  for (int i = threadIdx.x; i < count * ROW; i += 256) out[i] = s_out[(i / ROW) * ROWP + i % ROW];
 }
 
 template <typename T>
@@ -321,14 +429,18 @@ int weak_residual_local(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_
   if (frac && (!frac_det || !frac_jac || !frac_t)) return TFEM_ERR_BAD_ARG;
   const QuadT<T> quad = make_quad<T>(quad_order);
   const FracLite<T> fl{frac_jac, frac_inv, frac_det, frac_t};
-  const int threads = 256;
   auto s = static_cast<cudaStream_t>(stream);
-  if (frac)
-    weak_residual_local_kernel<T, true><<<blocks_for(n_el, threads), threads, 0, s>>>(
-        (int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, fl, src, f_q, grad_u, local_vec);
-  else
-    weak_residual_local_kernel<T, false><<<blocks_for(n_el, threads), threads, 0, s>>>(
-        (int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, fl, src, f_q, grad_u, local_vec);
+  const unsigned blocks = blocks_for(n_el, 256);
+#define TFEM_LAUNCH_FWD(F, Q)                                                                                   \
+  weak_residual_local_kernel<T, F, Q><<<blocks, 256, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, \
+                                                             fl, src, f_q, grad_u, local_vec)
+  switch (quad.n_q) {
+    case 1: if (frac) TFEM_LAUNCH_FWD(true, 1); else TFEM_LAUNCH_FWD(false, 1); break;
+    case 3: if (frac) TFEM_LAUNCH_FWD(true, 3); else TFEM_LAUNCH_FWD(false, 3); break;
+    case 4: if (frac) TFEM_LAUNCH_FWD(true, 4); else TFEM_LAUNCH_FWD(false, 4); break;
+    default: if (frac) TFEM_LAUNCH_FWD(true, 6); else TFEM_LAUNCH_FWD(false, 6); break;
+  }
+#undef TFEM_LAUNCH_FWD
   return check_launch();
 }
 
@@ -346,14 +458,18 @@ int weak_residual_bwd(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_me
   if (frac && !frac_det) return TFEM_ERR_BAD_ARG;
   const QuadT<T> quad = make_quad<T>(quad_order);
   const FracLite<T> fl{nullptr, frac_inv, frac_det, nullptr};
-  const int threads = 256;
   auto s = static_cast<cudaStream_t>(stream);
-  if (frac)
-    weak_residual_bwd_kernel<T, true><<<blocks_for(n_el, threads), threads, 0, s>>>(
-        (int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, dof_conn, quad, fl, r_bar, grad_u_bar);
-  else
-    weak_residual_bwd_kernel<T, false><<<blocks_for(n_el, threads), threads, 0, s>>>(
-        (int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, dof_conn, quad, fl, r_bar, grad_u_bar);
+  const unsigned blocks = blocks_for(n_el, 256);
+#define TFEM_LAUNCH_BWD(F, Q)                                                                                 \
+  weak_residual_bwd_kernel<T, F, Q><<<blocks, 256, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, dof_conn, \
+                                                           quad, fl, r_bar, grad_u_bar)
+  switch (quad.n_q) {
+    case 1: if (frac) TFEM_LAUNCH_BWD(true, 1); else TFEM_LAUNCH_BWD(false, 1); break;
+    case 3: if (frac) TFEM_LAUNCH_BWD(true, 3); else TFEM_LAUNCH_BWD(false, 3); break;
+    case 4: if (frac) TFEM_LAUNCH_BWD(true, 4); else TFEM_LAUNCH_BWD(false, 4); break;
+    default: if (frac) TFEM_LAUNCH_BWD(true, 6); else TFEM_LAUNCH_BWD(false, 6); break;
+  }
+#undef TFEM_LAUNCH_BWD
   return check_launch();
 }
 
@@ -394,3 +510,14 @@ int weak_residual_bwd(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_me
 
 TFEM_FORMS_API(double, f64)
 TFEM_FORMS_API(float, f32)
+
+#define TFEM_BATCHED_API(T, SUF)                                                                                  \
+  extern "C" int tfem_batched_weak_residual_##SUF(int64_t n_mesh, int n_el_per_mesh, int n_vert_per_mesh,         \
+                                                  const T* coords, const int32_t* conn, int quad_order,           \
+                                                  const tfem_source* host_source, const T* f_q, const T* grad_u,  \
+                                                  T* r, void* stream) {                                           \
+    return tfem::batched_weak_residual<T>(n_mesh, n_el_per_mesh, n_vert_per_mesh, coords, conn, quad_order,       \
+                                          host_source, f_q, grad_u, r, stream);                                   \
+  }
+TFEM_BATCHED_API(double, f64)
+TFEM_BATCHED_API(float, f32)

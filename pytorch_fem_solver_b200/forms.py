@@ -63,6 +63,11 @@ class SampledSource(Source):
 
     def __init__(self, function: Callable[[torch.Tensor], torch.Tensor]):
         self.function = function
+        self._samples = None  # (key, values at a basis' quadrature points), filled by AbstractBasis._sampled_source
+
+    def refresh(self):
+        """Forget cached samples (for a callable whose values change between calls)."""
+        self._samples = None
 
     def __call__(self, points):
         return self.function(points)

@@ -422,7 +422,19 @@ def weak_residual(
     frac_det: Optional[Tensor] = None,
     frac_t: Optional[Tensor] = None,
 ) -> Tensor:
-    """Global weak residual r (n_dof,): element kernel + deterministic scatter, two launches."""
+    """Global weak residual r (n_dof,): element kernel + deterministic scatter, two launches -- or ONE launch
+    (`tfem_batched_weak_residual`) for batches of small meshes with mesh-private DOFs (patches)."""
+    n_mesh = conn.shape[0] // n_el_per_mesh
+    if (frac_inv is None and n_el_per_mesh <= 8 and n_vert_per_mesh <= 16 and n_mesh > 1
+            and lin_seg.shape[0] - 1 == n_mesh * n_vert_per_mesh and n_mesh * n_el_per_mesh == conn.shape[0]):
+        device = check_cuda(grad_u, coords, conn, f_q)
+        n_q = _nq_tri(quad_order)
+        if tuple(grad_u.shape) != (conn.shape[0], n_q, 2):
+            raise TfemError(f"grad_u must have shape {(conn.shape[0], n_q, 2)}, got {tuple(grad_u.shape)}")
+        out = torch.empty((n_mesh * n_vert_per_mesh,), dtype=coords.dtype, device=device)
+        call("tfem_batched_weak_residual", coords.dtype, device, n_mesh, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn),
+             quad_order, make_source(source_kind, source_p), ptr(f_q), ptr(grad_u), ptr(out))
+        return out
     local = _weak_residual_local_launch(
         grad_u, coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, source_kind, source_p,
         f_q, frac_jac, frac_inv, frac_det, frac_t,

@@ -61,11 +61,33 @@ def residual_case(name, basis, n_el, n_q, d, size, flush, rows):
 
     t_f = timed(lambda: forward(), 20, flush)
     t_fb = timed(forward_backward, 20, flush)
+    # the same calls replayed from a CUDA graph: the device time without Python / dispatcher overhead, which is
+    # what a captured training step pays (the small patch case is otherwise bound by ~150 us of host work)
+    graphed = {}
+    for label, fn in (("forward", forward), ("forward+adjoint", forward_backward)):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            graphed[label] = timed(graph.replay, 20, flush)
+        except Exception as error:  # noqa: BLE001
+            graphed[label] = None
+            print(f"# graph capture of {name} {label} failed: {error!r}", file=sys.stderr)
     n_dof = r.numel()
     bytes_f = 12 * n_el + size * (d * n_q * n_el + n_q * n_el + n_dof) + size * 2 * n_dof  # conn + grad_u + f_q + r + coords
     bytes_b = 12 * n_el + size * (d * n_q * n_el + n_dof)
-    rows.append({"case": name + " forward", "elements": n_el, "us": round(t_f, 1), "GB/s": round(bytes_f / t_f / 1e3, 1)})
-    rows.append({"case": name + " forward+adjoint", "elements": n_el, "us": round(t_fb, 1), "GB/s": round((bytes_f + bytes_b) / t_fb / 1e3, 1)})
+    rows.append({"case": name + " forward", "elements": n_el, "us": round(t_f, 1), "GB/s": round(bytes_f / t_f / 1e3, 1),
+                 "us_graph_replay": None if graphed["forward"] is None else round(graphed["forward"], 1),
+                 "GB/s_graph_replay": None if graphed["forward"] is None else round(bytes_f / graphed["forward"] / 1e3, 1)})
+    rows.append({"case": name + " forward+adjoint", "elements": n_el, "us": round(t_fb, 1), "GB/s": round((bytes_f + bytes_b) / t_fb / 1e3, 1),
+                 "us_graph_replay": None if graphed["forward+adjoint"] is None else round(graphed["forward+adjoint"], 1),
+                 "GB/s_graph_replay": None if graphed["forward+adjoint"] is None else round((bytes_f + bytes_b) / graphed["forward+adjoint"] / 1e3, 1)})
 
 
 def main():
