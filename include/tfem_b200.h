@@ -220,6 +220,15 @@ int tfem_sm_count(void);
                                        const T* coords, const int32_t* conn, int quad_order,       \
                                        const tfem_source* host_source, const T* f_q,               \
                                        const T* grad_u, T* r, void* stream);                       \
+  /* H1 error functional of examples/example_weak.py:113-124 integrated by                       \
+   * basis/abstract_basis.py:65-72, fused (no integrand, no dx tensor):                          \
+   * out[e] = sum_q dx_q ((u_ex - u)^2 + |grad u_ex - grad u|^2); fields sampled at the           \
+   * quadrature points: u, u_ex [n_el,n_q]; grad_u, grad_ex [n_el,n_q,d]; frac_det [n_mesh] or   \
+   * NULL (planar). */                                                                           \
+  int tfem_h1_error_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh,            \
+                          const T* coords, const int32_t* conn, int quad_order, const T* frac_det, \
+                          int d, const T* u, const T* grad_u, const T* u_ex, const T* grad_ex,     \
+                          T* out, void* stream);                                                   \
   /* Basis.interpolate(self, u) (basis/basis.py:105-112,149-159; fracture_basis.py:214-223):     \
    * val[e,q] = sum_i u[dof_conn[e,i]] phi_i(q),  grad[e,:] = sum_i u[...] grad phi_i[e,:]. */    \
   int tfem_interp_cells_##SUF(int64_t n_el, const int32_t* dof_conn, const T* v_grad, int d,       \

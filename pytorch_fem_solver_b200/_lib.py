@@ -77,6 +77,7 @@ _TYPED = {
     "tfem_weak_residual_local": [I64, I64, I64, P, P, c_int, P, P, P, P, POINTER(Source), P, P, P, P],
     "tfem_weak_residual_bwd": [I64, I64, I64, P, P, P, c_int, P, P, P, P, P, P],
     "tfem_batched_weak_residual": [I64, c_int, c_int, P, P, c_int, POINTER(Source), P, P, P, P],
+    "tfem_h1_error": [I64, I64, I64, P, P, c_int, P, c_int, P, P, P, P, P, P],
     "tfem_interp_cells": [I64, P, P, c_int, c_int, P, P, P, P],
     "tfem_interp_edges": [I64, I64, I64, P, P, P, P, c_int, P, c_int, P, P, P, P],
     "tfem_interp_cells_bwd": [I64, P, c_int, c_int, P, P, P, P],

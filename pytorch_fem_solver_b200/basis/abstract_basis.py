@@ -206,10 +206,30 @@ class AbstractBasis(abc.ABC):
 
     def integrate_functional(self, function: Callable[..., torch.Tensor], *args: Any, **kwargs: Any) -> torch.Tensor:
         """Per-element integral `(f * dx).sum(-3).sum(-2)` -> (*lead, b) (reference :65-72)."""
+        if isinstance(function, forms.H1Error) and len(args) == 2 and not kwargs:
+            return self._h1_error_fused(function, *args)
         integrand = function(self, *args, **kwargs)
         a, b = integrand.shape[-2], integrand.shape[-1]
         local = self._reduce_integrand(integrand).reshape(*self._layout.lead, a, b)
         return local.sum(-2)
+
+    def _h1_error_fused(self, form, u, gradient) -> torch.Tensor:
+        """`forms.H1Error` in one kernel (`tfem_h1_error`): no integrand, no dx tensor."""
+        lay = self._layout
+        key = (id(self), self._geometry_version, self.dtype)
+        if form._samples is None or form._samples[0] != key:
+            with torch.no_grad():
+                points = self.integration_points
+                ue = form.exact(points).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+                ge = form.exact_grad(points).to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous()
+            form._samples = (key, ue, ge)
+        _, ue, ge = form._samples
+        uv = form.field(self, u).to(self.dtype).expand(*lay.lead, self.n_q, 1, 1).reshape(lay.n_total, self.n_q).contiguous()
+        gv = form.field(self, gradient).to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous()
+        frac_det = lay.frac_args()[2] if lay.frac is not None else None
+        out = ops.h1_error(uv.detach(), gv.detach(), ue, ge, lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh,
+                           self._element.integration_order, frac_det)
+        return out.reshape(*lay.lead, 1)
 
     def integrate_bilinear_form(
         self, function: Callable[..., torch.Tensor], *args: Any, layout: Optional[str] = None, **kwargs: Any
@@ -333,8 +353,24 @@ class AbstractBasis(abc.ABC):
         """Restrict to interior DOFs (reference :114-117)."""
         idx = self._basis_parameters["inner_dofs"]
         if tensor.layout == torch.sparse_csr:
-            tensor = tensor.to_dense()
+            return self._reduce_csr(tensor, idx)
         return tensor[idx, :][:, idx] if tensor.size(-1) != 1 else tensor[idx]
+
+    @staticmethod
+    def _reduce_csr(matrix: torch.Tensor, inner: torch.Tensor) -> torch.Tensor:
+        """`A[inner][:, inner]` of a CSR matrix as a CSR matrix in the compact interior numbering (the dense
+        fancy-indexing of the reference, abstract_basis.py:114-117, without densifying: config 2 would be 35 TB)."""
+        n = matrix.shape[-1]
+        crow, col, val = matrix.crow_indices(), matrix.col_indices(), matrix.values()
+        rank = torch.full((n,), -1, dtype=torch.int64, device=col.device)
+        rank[inner] = torch.arange(inner.numel(), device=col.device)
+        row_of = torch.repeat_interleave(torch.arange(n, device=col.device), (crow[1:] - crow[:-1]).long())
+        keep = (rank[row_of] >= 0) & (rank[col.long()] >= 0)
+        new_row = rank[row_of[keep]]
+        counts = torch.bincount(new_row, minlength=inner.numel())
+        new_crow = torch.zeros(inner.numel() + 1, dtype=crow.dtype, device=col.device)
+        new_crow[1:] = torch.cumsum(counts, 0)
+        return torch.sparse_csr_tensor(new_crow, rank[col.long()[keep]].to(col.dtype), val[keep], size=(inner.numel(), inner.numel()))
 
     def reshape_for_assembly(self, local_matrices: torch.Tensor, form: str) -> torch.Tensor:
         """Flatten local matrices in COO order (reference :162-171)."""

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(256) quad_reduce_kernel(int64_t total, int n_q
   local[i] = acc;
 }
 
+constexpr int kStagedBlock = 128;  // elements per block of the kernels that stage their streams through shared memory
+
 template <typename T>
 struct FracLite {
   const T* jac;  // [n_mesh,3,2]
@@ -128,12 +130,12 @@ __global__ void __launch_bounds__(256) local_forms_kernel(
 // (examples/example_weak.py:64-75 integrated by abstract_basis.py:95-104).  grad_u is the big
 // stream (n_q * d values per element) and is read exactly once.
 // ---------------------------------------------------------------------------------------------
-// The grad_u (and sampled f) rows of a block's 256 elements are copied to shared memory with fully
+// The grad_u (and sampled f) rows of a block of 128 elements are copied to shared memory with fully
 // coalesced loads (consecutive lanes, consecutive addresses) and read back row by row from a padded,
 // bank-conflict-free layout: the per-element stride in global memory (144 B for the 6-point rule on a
 // fracture) would otherwise make every warp load touch 32 different lines.
 template <typename T, bool FRAC, int NQ>
-__global__ void __launch_bounds__(256) weak_residual_local_kernel(
+__global__ void __launch_bounds__(kStagedBlock) weak_residual_local_kernel(
     int n_el, int n_el_per_mesh, int n_vert_per_mesh, const T* __restrict__ coords,
     const int32_t* __restrict__ conn, const QuadT<T> quad, const FracLite<T> frac,
     const SourceT<T> src, const T* __restrict__ f_q, const T* __restrict__ grad_u,
@@ -141,16 +143,16 @@ __global__ void __launch_bounds__(256) weak_residual_local_kernel(
   constexpr int D = FRAC ? 3 : 2;
   constexpr int ROW = NQ * D, ROWP = ROW | 1;  // odd stride: conflict-free rows
   constexpr int FROWP = NQ | 1;
-  __shared__ T s_gu[256 * ROWP];
-  __shared__ T s_f[256 * FROWP];
-  const int e0 = blockIdx.x * 256;
-  const int count = min(256, n_el - e0);
+  __shared__ T s_gu[kStagedBlock * ROWP];
+  __shared__ T s_f[kStagedBlock * FROWP];
+  const int e0 = blockIdx.x * kStagedBlock;
+  const int count = min(kStagedBlock, n_el - e0);
   {
     const T* g = grad_u + (int64_t)e0 * ROW;
-    for (int i = threadIdx.x; i < count * ROW; i += 256) s_gu[(i / ROW) * ROWP + i % ROW] = __ldg(g + i);
+    for (int i = threadIdx.x; i < count * ROW; i += kStagedBlock) s_gu[(i / ROW) * ROWP + i % ROW] = __ldg(g + i);
     if (src.kind == TFEM_SRC_SAMPLED) {
       const T* f = f_q + (int64_t)e0 * NQ;
-      for (int i = threadIdx.x; i < count * NQ; i += 256) s_f[(i / NQ) * FROWP + i % NQ] = __ldg(f + i);
+      for (int i = threadIdx.x; i < count * NQ; i += kStagedBlock) s_f[(i / NQ) * FROWP + i % NQ] = __ldg(f + i);
     }
   }
   __syncthreads();
@@ -315,17 +317,17 @@ int batched_weak_residual(int64_t n_mesh, int n_el_per_mesh, int n_vert_per_mesh
 
 // grad_u_bar[e,q,:] = -dx[e,q] * sum_i grad phi_i[e,:] * r_bar[dof_conn[e,i]]
 // Each thread lays its element's n_q * d values out in a padded shared-memory row; the block then writes
-// the 256 rows with fully coalesced stores.
+// the 128 rows with fully coalesced stores.
 template <typename T, bool FRAC, int NQ>
-__global__ void __launch_bounds__(256) weak_residual_bwd_kernel(
+__global__ void __launch_bounds__(kStagedBlock) weak_residual_bwd_kernel(
     int n_el, int n_el_per_mesh, int n_vert_per_mesh, const T* __restrict__ coords,
     const int32_t* __restrict__ conn, const int32_t* __restrict__ dof_conn, const QuadT<T> quad,
     const FracLite<T> frac, const T* __restrict__ r_bar, T* __restrict__ grad_u_bar) {
   constexpr int D = FRAC ? 3 : 2;
   constexpr int ROW = NQ * D, ROWP = ROW | 1;
-  __shared__ T s_out[256 * ROWP];
-  const int e0 = blockIdx.x * 256;
-  const int count = min(256, n_el - e0);
+  __shared__ T s_out[kStagedBlock * ROWP];
+  const int e0 = blockIdx.x * kStagedBlock;
+  const int count = min(kStagedBlock, n_el - e0);
   const int e = e0 + threadIdx.x;
   if (e < n_el) {
     const int mesh = e / n_el_per_mesh;
@@ -363,7 +365,75 @@ __global__ void __launch_bounds__(256) weak_residual_bwd_kernel(
   }
   __syncthreads();
   T* out = grad_u_bar + (int64_t)e0 * ROW;
-  for (int i = threadIdx.x; i < count * ROW; i += 256) out[i] = s_out[(i / ROW) * ROWP + i % ROW];
+  for (int i = threadIdx.x; i < count * ROW; i += kStagedBlock) out[i] = s_out[(i / ROW) * ROWP + i % ROW];
+}
+
+// ---------------------------------------------------------------------------------------------
+// H1 error functional of examples/example_weak.py:113-124 integrated by abstract_basis.py:65-72:
+//   out[e] = sum_q dx_q ( (u_ex - u)^2 + |grad u_ex - grad u|^2 )   at the element's quadrature points.
+// dx is recomputed from the coordinates (no weight tensor is read); the four fields are staged through
+// shared memory with coalesced loads like the residual kernel's grad_u.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int D, int NQ>
+__global__ void __launch_bounds__(kStagedBlock) h1_error_kernel(int n_el, int n_el_per_mesh, int n_vert_per_mesh,
+                                                       const T* __restrict__ coords, const int32_t* __restrict__ conn,
+                                                       const QuadT<T> quad, const T* __restrict__ frac_det,
+                                                       const T* __restrict__ u, const T* __restrict__ grad_u,
+                                                       const T* __restrict__ u_ex, const T* __restrict__ grad_ex,
+                                                       T* __restrict__ out) {
+  constexpr int ROW = NQ * (D + 1), ROWP = ROW | 1;
+  __shared__ T s_d[kStagedBlock * ROWP];  // per element: (u_ex - u)[NQ], (grad_ex - grad_u)[NQ * D]
+  const int e0 = blockIdx.x * kStagedBlock;
+  const int count = min(kStagedBlock, n_el - e0);
+  for (int i = threadIdx.x; i < count * NQ; i += kStagedBlock)
+    s_d[(i / NQ) * ROWP + i % NQ] = __ldg(u_ex + (int64_t)e0 * NQ + i) - __ldg(u + (int64_t)e0 * NQ + i);
+  for (int i = threadIdx.x; i < count * NQ * D; i += kStagedBlock)
+    s_d[(i / (NQ * D)) * ROWP + NQ + i % (NQ * D)] = __ldg(grad_ex + (int64_t)e0 * NQ * D + i) - __ldg(grad_u + (int64_t)e0 * NQ * D + i);
+  __syncthreads();
+  const int e = e0 + threadIdx.x;
+  if (e >= n_el) return;
+  const int mesh = e / n_el_per_mesh;
+  const int64_t voff = (int64_t)mesh * n_vert_per_mesh;
+  T x0, y0, x1, y1, x2, y2;
+  load_xy(coords, voff + __ldg(conn + 3 * (int64_t)e + 0), x0, y0);
+  load_xy(coords, voff + __ldg(conn + 3 * (int64_t)e + 1), x1, y1);
+  load_xy(coords, voff + __ldg(conn + 3 * (int64_t)e + 2), x2, y2);
+  T det = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+  if (frac_det) det *= __ldg(frac_det + mesh);
+  const T* row = s_d + threadIdx.x * ROWP;
+  T acc = T(0);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    T sq = row[q] * row[q];
+#pragma unroll
+    for (int c = 0; c < D; ++c) sq += row[NQ + q * D + c] * row[NQ + q * D + c];
+    acc += (quad.w[q] * det) * sq;
+  }
+  out[e] = acc;
+}
+
+template <typename T>
+int h1_error(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh, const T* coords, const int32_t* conn, int quad_order,
+             const T* frac_det, int d, const T* u, const T* grad_u, const T* u_ex, const T* grad_ex, T* out, void* stream) {
+  if (n_el < 0 || n_el_per_mesh <= 0 || n_vert_per_mesh <= 0 || (d != 2 && d != 3)) return TFEM_ERR_BAD_ARG;
+  if (n_el == 0) return TFEM_OK;
+  if (!coords || !conn || !u || !grad_u || !u_ex || !grad_ex || !out) return TFEM_ERR_BAD_ARG;
+  if (n_el > kMaxIndex / 24) return TFEM_ERR_TOO_LARGE;
+  if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
+  const QuadT<T> quad = make_quad<T>(quad_order);
+  auto s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = blocks_for(n_el, kStagedBlock);
+#define TFEM_LAUNCH_H1(DD, Q)                                                                                                  \
+  h1_error_kernel<T, DD, Q><<<blocks, kStagedBlock, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, frac_det, u, \
+                                                   grad_u, u_ex, grad_ex, out)
+  switch (quad.n_q) {
+    case 1: if (d == 3) TFEM_LAUNCH_H1(3, 1); else TFEM_LAUNCH_H1(2, 1); break;
+    case 3: if (d == 3) TFEM_LAUNCH_H1(3, 3); else TFEM_LAUNCH_H1(2, 3); break;
+    case 4: if (d == 3) TFEM_LAUNCH_H1(3, 4); else TFEM_LAUNCH_H1(2, 4); break;
+    default: if (d == 3) TFEM_LAUNCH_H1(3, 6); else TFEM_LAUNCH_H1(2, 6); break;
+  }
+#undef TFEM_LAUNCH_H1
+  return check_launch();
 }
 
 template <typename T>
@@ -430,9 +500,9 @@ int weak_residual_local(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_
   const QuadT<T> quad = make_quad<T>(quad_order);
   const FracLite<T> fl{frac_jac, frac_inv, frac_det, frac_t};
   auto s = static_cast<cudaStream_t>(stream);
-  const unsigned blocks = blocks_for(n_el, 256);
+  const unsigned blocks = blocks_for(n_el, kStagedBlock);
 #define TFEM_LAUNCH_FWD(F, Q)                                                                                   \
-  weak_residual_local_kernel<T, F, Q><<<blocks, 256, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, \
+  weak_residual_local_kernel<T, F, Q><<<blocks, kStagedBlock, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, quad, \
                                                              fl, src, f_q, grad_u, local_vec)
   switch (quad.n_q) {
     case 1: if (frac) TFEM_LAUNCH_FWD(true, 1); else TFEM_LAUNCH_FWD(false, 1); break;
@@ -459,9 +529,9 @@ int weak_residual_bwd(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_me
   const QuadT<T> quad = make_quad<T>(quad_order);
   const FracLite<T> fl{nullptr, frac_inv, frac_det, nullptr};
   auto s = static_cast<cudaStream_t>(stream);
-  const unsigned blocks = blocks_for(n_el, 256);
+  const unsigned blocks = blocks_for(n_el, kStagedBlock);
 #define TFEM_LAUNCH_BWD(F, Q)                                                                                 \
-  weak_residual_bwd_kernel<T, F, Q><<<blocks, 256, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, dof_conn, \
+  weak_residual_bwd_kernel<T, F, Q><<<blocks, kStagedBlock, 0, s>>>((int)n_el, (int)n_el_per_mesh, (int)n_vert_per_mesh, coords, conn, dof_conn, \
                                                            quad, fl, r_bar, grad_u_bar)
   switch (quad.n_q) {
     case 1: if (frac) TFEM_LAUNCH_BWD(true, 1); else TFEM_LAUNCH_BWD(false, 1); break;
@@ -521,3 +591,13 @@ TFEM_FORMS_API(float, f32)
   }
 TFEM_BATCHED_API(double, f64)
 TFEM_BATCHED_API(float, f32)
+
+#define TFEM_H1_API(T, SUF)                                                                                          \
+  extern "C" int tfem_h1_error_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh, const T* coords,  \
+                                     const int32_t* conn, int quad_order, const T* frac_det, int d, const T* u,      \
+                                     const T* grad_u, const T* u_ex, const T* grad_ex, T* out, void* stream) {       \
+    return tfem::h1_error<T>(n_el, n_el_per_mesh, n_vert_per_mesh, coords, conn, quad_order, frac_det, d, u, grad_u, \
+                             u_ex, grad_ex, out, stream);                                                            \
+  }
+TFEM_H1_API(double, f64)
+TFEM_H1_API(float, f32)

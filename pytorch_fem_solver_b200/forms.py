@@ -11,6 +11,7 @@ Forms covered:
   Load(source)                       tests/test_assembly.py:79-84
   WeakResidual(source)               examples/example_weak.py:64-75, example_patches.py:102-113,
                                      example_fracture_vpinns.py:104-113
+  H1Error(exact, exact_grad)         examples/example_weak.py:113-124
 """
 
 from __future__ import annotations
@@ -142,6 +143,31 @@ class WeakResidual:
     def __call__(self, basis, gradient):
         grad = self.field(basis, gradient)
         return self.source(basis.integration_points) * basis.v - basis.v_grad @ grad.mT
+
+
+class H1Error:
+    """(u_ex - u)^2 + |grad u_ex - grad u|^2 of examples/example_weak.py:113-124:
+    `basis.integrate_functional(H1Error(exact, exact_grad), neural_network, neural_network.gradient)`.
+
+    `exact(points) -> (..., 1)` and `exact_grad(points) -> (..., d)` are sampled once per basis (the points do not
+    move); `u` / `gradient` are callables of the points or tensors of their values."""
+
+    def __init__(self, exact: Callable[[torch.Tensor], torch.Tensor], exact_grad: Callable[[torch.Tensor], torch.Tensor]):
+        self.exact, self.exact_grad = exact, exact_grad
+        self._samples = None
+
+    def refresh(self):
+        self._samples = None
+
+    @staticmethod
+    def field(basis, value) -> torch.Tensor:
+        return value(basis.integration_points) if callable(value) else value
+
+    def __call__(self, basis, u, gradient):
+        points = basis.integration_points
+        diff = self.exact(points) - self.field(basis, u)
+        diff_grad = self.exact_grad(points) - self.field(basis, gradient)
+        return diff**2 + (diff_grad**2).sum(-1, keepdim=True)
 
 
 class Jump:

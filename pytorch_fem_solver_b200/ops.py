@@ -471,6 +471,25 @@ def _weak_residual_backward(ctx, r_bar):
 weak_residual.register_autograd(_weak_residual_backward, setup_context=_weak_residual_setup)
 
 
+@torch.library.custom_op(f"{NS}::h1_error", mutates_args=())
+def h1_error(u: Tensor, grad_u: Tensor, u_ex: Tensor, grad_ex: Tensor, coords: Tensor, conn: Tensor, n_el_per_mesh: int,
+             n_vert_per_mesh: int, quad_order: int, frac_det: Optional[Tensor] = None) -> Tensor:
+    """Per-element H1 error sum_q dx ((u_ex - u)^2 + |grad_ex - grad_u|^2): fields (N,q) / (N,q,d) -> (N,)."""
+    device = check_cuda(u, grad_u, u_ex, grad_ex, coords, conn, frac_det)
+    n_el, n_q, d = grad_u.shape
+    if n_q != _nq_tri(quad_order) or tuple(u.shape) != (n_el, n_q) or u_ex.shape != u.shape or grad_ex.shape != grad_u.shape:
+        raise TfemError("h1_error: fields must be (N, n_q) and (N, n_q, d) at the basis' quadrature points")
+    out = torch.empty((n_el,), dtype=coords.dtype, device=device)
+    call("tfem_h1_error", coords.dtype, device, n_el, n_el_per_mesh, n_vert_per_mesh, ptr(coords), ptr(conn), quad_order,
+         ptr(frac_det), d, ptr(u), ptr(grad_u), ptr(u_ex), ptr(grad_ex), ptr(out))
+    return out
+
+
+@h1_error.register_fake
+def _(u, grad_u, u_ex, grad_ex, coords, conn, n_el_per_mesh, n_vert_per_mesh, quad_order, frac_det=None):
+    return coords.new_empty((conn.shape[0],))
+
+
 # ------------------------------------------------------------------------------------------------
 # interpolation / jump
 # ------------------------------------------------------------------------------------------------

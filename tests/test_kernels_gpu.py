@@ -433,3 +433,48 @@ def test_host_pipeline_matches_direct_assembly():
         torch.cuda.synchronize()
         assert torch.equal(values, ref_values) and torch.equal(vec, ref_vec)
     assert not torch.equal(outs[0][0], outs[1][0])  # the steps really had different inputs
+
+
+def test_h1_error_functional_fused_matches_generic():
+    """examples/example_weak.py:113-124: the fused kernel against the generic integrand path and the oracle."""
+    import math
+
+    mesh = meshgen.structured_rectangle(40, 30, jitter=0.2, seed=3, topology=False)
+    for order in (2, 3, 4):
+        basis = make_basis(mesh, order)
+
+        def exact(p):
+            return torch.sin(math.pi * p[..., 0:1]) * torch.sin(math.pi * p[..., 1:2])
+
+        def exact_grad(p):
+            return math.pi * torch.cat([torch.cos(math.pi * p[..., 0:1]) * torch.sin(math.pi * p[..., 1:2]),
+                                        torch.sin(math.pi * p[..., 0:1]) * torch.cos(math.pi * p[..., 1:2])], dim=-1)
+
+        def u(p):
+            return p[..., 0:1] * (1 - p[..., 0:1]) * p[..., 1:2] ** 2
+
+        def gradient(p):
+            x, y = p[..., 0:1], p[..., 1:2]
+            return torch.cat([(1 - 2 * x) * y**2, 2 * x * (1 - x) * y], dim=-1)
+
+        form = forms.H1Error(exact, exact_grad)
+        fused = basis.integrate_functional(form, u, gradient)
+        generic = basis.integrate_functional(lambda b, a, g: form(b, a, g), u, gradient)
+        assert fused.shape == generic.shape
+        assert relmax(fused.cpu().numpy(), generic.cpu().numpy()) < 1e-12
+        geo = fo.tri_geometry(mesh["vertices"], mesh["triangles"], order)
+        pts = torch.from_numpy(geo["integration_points"])
+        integrand = (form(type("B", (), {"integration_points": pts})(), u, gradient)).numpy()
+        ref = fo.integrate_functional(integrand, geo["dx"])
+        assert relmax(fused.cpu().numpy(), ref) < 1e-12
+
+
+def test_reduce_keeps_csr_sparse():
+    """`reduce` of a CSR operator returns the interior block in compact numbering without densifying."""
+    mesh = meshgen.structured_rectangle(12, 9, jitter=0.2, seed=1)
+    basis = make_basis(mesh, 3)
+    dense = basis.integrate_bilinear_form(forms.StiffnessMass(), layout="dense")
+    csr_matrix = basis.integrate_bilinear_form(forms.StiffnessMass(), layout="csr")
+    reduced = basis.reduce(csr_matrix)
+    assert reduced.layout == torch.sparse_csr
+    assert torch.equal(reduced.to_dense(), basis.reduce(dense))
