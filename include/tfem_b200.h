@@ -81,6 +81,7 @@ typedef struct tfem_bilinear {
  *     seg_start[n_segs] u32 csr_val offset of the first entry of each segment: a run of consecutive CSR
  *                      rows cut into pieces of at most 32 entries (one warp pass each)
  *     row_id[n_rows]   u32  global row (DOF) of each owned row, ascending
+ *     elem_id[n_elem]  u32  (only with has_elem_ids) global id of each tile element, in the order of elem[]
  *   template, part TB (integration phase)
  *     header[8]        n_vert, n_elem, n_rows, n_segs, n_chunks, n_heavy, n_heavy_contrib, 0
  *     elem[n_elem]     u32  tile-local connectivity  v0 | v1<<10 | v2<<20
@@ -122,6 +123,8 @@ typedef struct tfem_tile_plan {
   const int32_t* tpl_desc;   /* [templates][4]: TB word offset, TB words, TC word offset, TC words */
   const int32_t* tpl_blob;
   int32_t max_vert, max_elem, max_inst_words, max_tb_words, max_tc_words; /* per-tile maxima (shared-memory sizing) */
+  int32_t has_elem_ids;     /* instances end with elem_id[n_elem]: the global id of every tile element in elem[] order
+                               (needed by tfem_tri_p1_assemble_csr_ex with a sampled source or fracture metrics) */
   int32_t table_bytes;      /* size of the CTA's local table in fp64 bytes (the fp32 kernels use half) */
   int32_t od_base[3];       /* byte offsets of the off-diagonal arrays K01, K12, K20 inside the table (see below) */
   int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = library default (384) */
@@ -194,6 +197,19 @@ int tfem_sm_count(void);
                                      int quad_order, const tfem_bilinear* host_form,               \
                                      const tfem_source* host_source, T* csr_val, T* load,          \
                                      void* stream);                                                \
+  /* The same launch for sources given AT THE QUADRATURE POINTS and for fracture networks:        \
+   * f_q [n_el, n_q] (host_source->kind == TFEM_SRC_SAMPLED; what `Load(callable)` of every       \
+   * reference call site reduces to, tests/test_assembly.py:79-84,                                \
+   * examples/example_fractures_fem.py:102-116) is read per tile element through the plan's       \
+   * elem_id section; frac_metric [n_mesh, 4] = (a00, a01, a11, det J_f) with                     \
+   * a = J_f^+ J_f^+^T turns the planar forms into the tangential ones of                         \
+   * basis/fracture_basis.py:20-26,189-197 (element e lies on fracture e / n_el_per_mesh).        \
+   * Both NULL: identical to tfem_tri_p1_assemble_csr. */                                         \
+  int tfem_tri_p1_assemble_csr_ex_##SUF(const tfem_tile_plan* host_plan, const T* coords,          \
+                                        int quad_order, const tfem_bilinear* host_form,            \
+                                        const tfem_source* host_source, const T* f_q,              \
+                                        int64_t n_el_per_mesh, const T* frac_metric, T* csr_val,   \
+                                        T* load, void* stream);                                    \
   /* Weak residual r_i = sum_q dx (f phi_i - grad phi_i . grad u) of                              \
    * examples/example_weak.py:64-75 / example_patches.py:102-113 /                               \
    * example_fracture_vpinns.py:104-113 integrated by basis/abstract_basis.py:95-112:            \

@@ -55,6 +55,7 @@ class TilePlan(Structure):
         ("max_inst_words", c_int32),
         ("max_tb_words", c_int32),
         ("max_tc_words", c_int32),
+        ("has_elem_ids", c_int32),
         ("table_bytes", c_int32),
         ("od_base", c_int32 * 3),
         ("consumer_threads", c_int32),
@@ -74,6 +75,7 @@ _TYPED = {
     "tfem_scatter_linear": [I64, P, P, P, P, P],
     "tfem_tri_p1_local_forms": [I64, I64, I64, P, P, c_int, P, P, P, P, POINTER(Bilinear), POINTER(Source), P, P, P, P],
     "tfem_tri_p1_assemble_csr": [POINTER(TilePlan), P, c_int, POINTER(Bilinear), POINTER(Source), P, P, P],
+    "tfem_tri_p1_assemble_csr_ex": [POINTER(TilePlan), P, c_int, POINTER(Bilinear), POINTER(Source), P, I64, P, P, P, P],
     "tfem_weak_residual_local": [I64, I64, I64, P, P, c_int, P, P, P, P, POINTER(Source), P, P, P, P],
     "tfem_weak_residual_bwd": [I64, I64, I64, P, P, P, c_int, P, P, P, P, P, P],
     "tfem_batched_weak_residual": [I64, c_int, c_int, P, P, c_int, POINTER(Source), P, P, P, P],

@@ -153,20 +153,38 @@ class AbstractBasis(abc.ABC):
             self._scatter_inverse[kind] = inverse
         return self._scatter_inverse[kind]
 
-    def tile_plan(self, rows_per_tile: int = 336, ordering: str = "auto"):
-        """Row-tile plan of the fused assembly kernel (planar meshes), cached per setting."""
-        key = (rows_per_tile, ordering)
+    def tile_plan(self, rows_per_tile: int = 336, ordering: str = "auto", elem_ids: Optional[bool] = None):
+        """Row-tile plan of the fused assembly kernel, cached per setting.  `elem_ids`: the instances carry the
+        global id of every tile element (sampled sources, fracture networks); default: only where needed."""
+        lay = self._layout
+        if elem_ids is None:
+            elem_ids = lay.frac is not None
+        key = (rows_per_tile, ordering, bool(elem_ids))
         if key not in self._tile_plans:
-            lay = self._layout
-            if lay.frac is not None:
-                raise NotImplementedError("the tiled kernel covers planar meshes; fractures use local_forms + scatter")
             offsets = (torch.arange(lay.n_total, device=lay.conn.device) // lay.n_el_per_mesh) * lay.n_vert_per_mesh
             geom_conn = lay.conn.long() + offsets[:, None]
             dof_conn = self._dof_conn_flat()
             points = torch.zeros((self.n_dof_flat, 2), dtype=lay.coords.dtype, device=lay.coords.device)
-            points[dof_conn.reshape(-1).long()] = lay.coords[geom_conn.reshape(-1)]
-            self._tile_plans[key] = csr_mod.build_tile_plan(geom_conn, dof_conn, self.pattern, points, rows_per_tile, ordering)
+            local = lay.coords[geom_conn.reshape(-1)].clone()
+            if lay.n_total > lay.n_el_per_mesh:  # batched meshes share one local frame: keep them apart when clustering rows
+                span = float(lay.coords[:, 0].max() - lay.coords[:, 0].min())  # side by side, no gaps: the blocks stay full
+                local[:, 0] += span * (offsets.repeat_interleave(3) // lay.n_vert_per_mesh).to(local.dtype)
+            points[dof_conn.reshape(-1).long()] = local
+            self._tile_plans[key] = csr_mod.build_tile_plan(geom_conn, dof_conn, self.pattern, points, rows_per_tile, ordering,
+                                                            elem_ids=bool(elem_ids))
         return self._tile_plans[key]
+
+    def _fracture_metric(self) -> Optional[torch.Tensor]:
+        """(n_mesh, 4) = (a00, a01, a11, det J_f) with a = J_f^+ J_f^+^T: the metric in which the planar element
+        vectors give the tangential gradients' inner products (fracture_basis.py:20-26)."""
+        lay = self._layout
+        if lay.frac is None:
+            return None
+        if getattr(self, "_frac_metric", None) is None:
+            inv, det = lay.frac[1], lay.frac[2]  # (F,2,3), (F,)
+            a = inv @ inv.mT
+            self._frac_metric = torch.stack([a[:, 0, 0], a[:, 0, 1], a[:, 1, 1], det.reshape(-1)], dim=1).to(self.dtype).contiguous()
+        return self._frac_metric
 
     def _sampled_source(self, src) -> torch.Tensor:
         """f at this basis' quadrature points, (N_total, n_q).  The points of a basis are fixed, so the samples of
@@ -314,15 +332,17 @@ class AbstractBasis(abc.ABC):
         want_mat = bilinear is not None
         want_vec = source is not None
         alpha, beta = (bilinear.alpha, bilinear.beta) if want_mat else (0.0, 0.0)
-        tiled_ok = lay.frac is None and src.kind != ops.SRC_SAMPLED
+        sampled = want_vec and src.kind == ops.SRC_SAMPLED
+        # one launch for everything but analytic (x, y) sources on fractures, which the kernels evaluate in 3-D
+        tiled_ok = lay.frac is None or not want_vec or src.kind in (ops.SRC_SAMPLED, ops.SRC_CONST, ops.SRC_NONE)
         if path == "tiled" and not tiled_ok:
-            raise NotImplementedError("tiled assembly needs a planar mesh and an analytic source")
+            raise NotImplementedError("tiled assembly on a fracture network needs a sampled or constant source")
         if path == "tiled" or (path == "auto" and tiled_ok):
-            plan = self.tile_plan()
+            plan = self.tile_plan(elem_ids=sampled or lay.frac is not None)
             values = torch.empty(pat.nnz, dtype=self.dtype, device=self.device) if want_mat else None
             vec = torch.empty(pat.n_dof, dtype=self.dtype, device=self.device) if want_vec else None
-            ops.assemble_csr_tiled(plan.c_struct(), lay.coords, order, alpha, beta, src.kind if want_vec else 0,
-                                   src.params, values, vec)
+            ops.assemble_csr_tiled(plan, lay.coords, order, alpha, beta, src.kind if want_vec else 0, src.params, values, vec,
+                                   self._sampled_source(src) if sampled else None, lay.n_el_per_mesh, self._fracture_metric())
             return values, vec
         f_q = self._sampled_source(src) if want_vec and src.kind == ops.SRC_SAMPLED else None
         local_mat, local_vec = ops.local_forms(

@@ -361,6 +361,9 @@ struct TiledArgs {
   int od_base[3];  // byte offsets (in units of T: already scaled) of the off-diagonal arrays inside the table
   uint32_t* progress;
   const T* coords;
+  const T* f_q;          // [n_el, n_q] source at the quadrature points (TFEM_SRC_SAMPLED), via the instances' elem_id section
+  const T* frac_metric;  // [n_mesh, 4] (a00, a01, a11, det J_f) or NULL; element e lies on fracture e / n_el_per_mesh
+  int n_el_per_mesh;
   SourceT<T> src;
   T* csr_val;
   T* load;
@@ -374,12 +377,14 @@ struct TiledArgs {
 template <int CONSUMERS>
 struct MinCtas { static constexpr int value = CONSUMERS <= 256 ? 3 : 2; };
 
-template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
+template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT, bool FRAC>
 __global__ void __launch_bounds__(CONSUMERS + 32, MinCtas<CONSUMERS>::value)
 assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const QuadT<T> quad) {
   constexpr int NQV = NQ<ORDER>::value;
   constexpr bool HAS_LOAD = SRC != TFEM_SRC_NONE;
   constexpr bool SINSIN = SRC == TFEM_SRC_SINSIN;
+  constexpr bool SAMPLED = SRC == TFEM_SRC_SAMPLED;
+  constexpr bool NEED_IDS = SAMPLED || FRAC;
   constexpr int kWarps = CONSUMERS / 32;
   constexpr uint32_t kRowBytes = kDlSlots * sizeof(T);
   constexpr uint32_t kS = sizeof(T);
@@ -555,6 +560,8 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
     const int tc_gen = rec_a.x, n_vert = rec_a.y, n_elem = rec_a.z, n_rows = rec_a.w;
     const int n_segs = rec_b.x, n_chunks = rec_b.y, n_heavy = rec_b.z, n_heavy_contrib = rec_b.w;
     const uint32_t a_xy = smem_u32(vxy + stage * args.max_vert);
+    // elem_id[n_elem] closes the instance (include/tfem_b200.h)
+    const uint32_t a_eid = smem_u32(s_inst + (it % kInstStages) * args.inst_words) + 4u * (uint32_t)(kInstHeader + pad4(n_vert) + pad4(n_segs) + pad4(n_rows));
     TFEM_T(1);
 
     // ---- B: local matrices and loads, each tile element once ----------------------------------
@@ -564,9 +571,24 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
       // below need every lane)
       const int el = base + lane;
       const bool valid = el < n_elem;
-      const uint32_t packed = lds_u32(a_elem + 4u * (uint32_t)(valid ? el : n_elem - 1));
+      const uint32_t slot = (uint32_t)(valid ? el : n_elem - 1);
+      const uint32_t packed = lds_u32(a_elem + 4u * slot);
       const uint32_t row = (uint32_t)(valid ? el + 1 : args.max_elem + 1);
       const uint32_t out = a_tab + row * kRowBytes;
+      // sampled source / fracture metric of this element, fetched first so the loads overlap the geometry
+      T fq[NQV];
+      T a00 = T(1), a01 = T(0), a11 = T(1), detf = T(1);
+      if constexpr (NEED_IDS) {
+        const int64_t eid = (int64_t)lds_u32(a_eid + 4u * slot);
+        if constexpr (SAMPLED) {
+#pragma unroll
+          for (int q = 0; q < NQV; ++q) fq[q] = __ldg(args.f_q + eid * NQV + q);
+        }
+        if constexpr (FRAC) {
+          const T* metric = args.frac_metric + 4 * (eid / args.n_el_per_mesh);
+          a00 = __ldg(metric); a01 = __ldg(metric + 1); a11 = __ldg(metric + 2); detf = __ldg(metric + 3);
+        }
+      }
       T x0, y0, x1, y1, x2, y2;
       lds_2(a_xy + (packed & 1023u) * (2 * kS), x0, y0);
       lds_2(a_xy + ((packed >> 10) & 1023u) * (2 * kS), x1, y1);
@@ -574,14 +596,25 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
       const T ax = x1 - x0, ay = y1 - y0;  // J = [[ax, bx], [ay, by]] (basis.py:87-88)
       const T bx = x2 - x0, by = y2 - y0;
       const T det = ax * by - bx * ay;  // signed (element_tri.py:139)
-      const T s11 = fma(by, by, bx * bx), s22 = fma(ay, ay, ax * ax);  // squared edge lengths
+      // e_1 = (by, -bx), e_2 = (-ay, ax): e_i . e_j, on a fracture in the metric a = J_f^+ J_f^+^T of the plane
+      T s11, s22;
+      if constexpr (FRAC) {
+        s11 = fma(a00 * by, by, fma(a11 * bx, bx, T(-2) * (a01 * by) * bx));
+        s22 = fma(a00 * ay, ay, fma(a11 * ax, ax, T(-2) * (a01 * ay) * ax));
+      } else {
+        s11 = fma(by, by, bx * bx);
+        s22 = fma(ay, ay, ax * ax);  // squared edge lengths
+      }
       T k00 = T(0), k11 = T(0), k22 = T(0), k01 = T(0), k12 = T(0), k20 = T(0), b0 = T(0), b1 = T(0), b2 = T(0);
       if constexpr (HAS_MAT) {
         // grad(phi_i) = e_i / det with e_1 = (by, -bx), e_2 = (-ay, ax), e_0 = -e_1 - e_2, so
         // sum_q dx grad(phi_i).grad(phi_j) = (wsum / det) e_i.e_j ; mass = det * reference mass
-        const T kc = cst.kcw * fast_rcp(det);
-        const T md = det * cst.md, mo = det * cst.mo;
-        const T s12 = -fma(by, ay, bx * ax);
+        const T kc = (FRAC ? cst.kcw * detf : cst.kcw) * fast_rcp(det);
+        const T area = FRAC ? det * detf : det;
+        const T md = area * cst.md, mo = area * cst.mo;
+        T s12;
+        if constexpr (FRAC) s12 = fma(a01, fma(by, ax, bx * ay), -fma(a00 * by, ay, (a11 * bx) * ax));
+        else s12 = -fma(by, ay, bx * ax);
         const T s01 = -s11 - s12, s02 = -s22 - s12, s00 = -s01 - s02;
         k00 = fma(kc, s00, md);
         k11 = fma(kc, s11, md);
@@ -652,10 +685,17 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
               }
             }
           }
+        } else if constexpr (SAMPLED) {  // f given at the element's quadrature points
+#pragma unroll
+          for (int q = 0; q < NQV; ++q) {
+            b0 = fma(cst.wl0[q], fq[q], b0);
+            b1 = fma(cst.wl1[q], fq[q], b1);
+            b2 = fma(cst.wl2[q], fq[q], b2);
+          }
         } else {  // constant source: the moments of the basis functions are constants
           b0 = cst.m0; b1 = cst.m1; b2 = cst.m2;
         }
-        const T amp = args.src.p0 * det;
+        const T amp = (SAMPLED ? T(1) : args.src.p0) * (FRAC ? det * detf : det);
         b0 *= amp; b1 *= amp; b2 *= amp;
       }
       sts_2(out, k00, b0);
@@ -770,7 +810,7 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
 #endif
 }
 
-template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT>
+template <typename T, int CONSUMERS, int ORDER, int SRC, bool HAS_MAT, bool FRAC = false>
 int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledConst<T>& cst, const QuadT<T>& quad, cudaStream_t s) {
   args.inst_words = pad4(hp->max_inst_words);
   args.tb_words = pad4(hp->max_tb_words);
@@ -778,7 +818,7 @@ int launch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledConst<
   const size_t smem = kSmemHeader + 4 * ((size_t)kInstStages * args.inst_words + (size_t)args.tb_words + (size_t)args.tc_words) +
                       sizeof(T) * ((size_t)2 * kStages * hp->max_vert) + (size_t)hp->table_bytes / 8 * sizeof(T);
   if (smem > 227 * 1024) return TFEM_ERR_TOO_LARGE;
-  auto kern = assemble_tiled_kernel<T, CONSUMERS, ORDER, SRC, HAS_MAT>;
+  auto kern = assemble_tiled_kernel<T, CONSUMERS, ORDER, SRC, HAS_MAT, FRAC>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return TFEM_ERR_LAUNCH;
   int dev = 0, sms = 0, per_sm = 0;
@@ -802,6 +842,21 @@ int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledCons
   }
   return TFEM_ERR_UNSUPPORTED;
 #else
+  if (args.frac_metric) {  // fracture network: tangential forms; analytic sources live in 3-D and come sampled
+    if (args.csr_val) {
+      if (kind == TFEM_SRC_SAMPLED) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, true, true>(hp, args, cst, quad, s);
+      if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true, true>(hp, args, cst, quad, s);
+      if (kind == TFEM_SRC_NONE) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_NONE, true, true>(hp, args, cst, quad, s);
+      return TFEM_ERR_UNSUPPORTED;
+    }
+    if (kind == TFEM_SRC_SAMPLED) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, false, true>(hp, args, cst, quad, s);
+    if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, false, true>(hp, args, cst, quad, s);
+    return TFEM_ERR_UNSUPPORTED;
+  }
+  if (kind == TFEM_SRC_SAMPLED) {
+    if (args.csr_val) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, true>(hp, args, cst, quad, s);
+    return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, false>(hp, args, cst, quad, s);
+  }
   if (args.csr_val) {
     if (kind == TFEM_SRC_SINSIN) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SINSIN, true>(hp, args, cst, quad, s);
     if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true>(hp, args, cst, quad, s);
@@ -815,7 +870,8 @@ int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledCons
 
 template <typename T>
 int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, const tfem_bilinear* form,
-                   const tfem_source* source, T* csr_val, T* load, void* stream) {
+                   const tfem_source* source, const T* f_q, int64_t n_el_per_mesh, const T* frac_metric, T* csr_val, T* load,
+                   void* stream) {
   if (!hp || hp->n_tiles < 0) return TFEM_ERR_BAD_ARG;
   if (hp->n_tiles == 0) return TFEM_OK;
   if (!coords || (!csr_val && !load)) return TFEM_ERR_BAD_ARG;
@@ -830,8 +886,14 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
   if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
   TiledArgs<T> args{};
   args.src = make_source<T>(source);
-  if (load && (args.src.kind == TFEM_SRC_SAMPLED || args.src.kind < TFEM_SRC_NONE || args.src.kind > TFEM_SRC_SINSIN))
-    return TFEM_ERR_BAD_ARG;  // sampled sources go through tfem_tri_p1_local_forms
+  if (load && (args.src.kind < TFEM_SRC_NONE || args.src.kind > TFEM_SRC_SINSIN)) return TFEM_ERR_BAD_ARG;
+  const bool sampled = load && args.src.kind == TFEM_SRC_SAMPLED;
+  if (sampled && !f_q) return TFEM_ERR_BAD_ARG;
+  if ((sampled || frac_metric) && !hp->has_elem_ids) return TFEM_ERR_BAD_ARG;  // the plan must carry element ids
+  if (frac_metric && n_el_per_mesh <= 0) return TFEM_ERR_BAD_ARG;
+  args.f_q = f_q;
+  args.frac_metric = frac_metric;
+  args.n_el_per_mesh = (int)(n_el_per_mesh > 0 ? n_el_per_mesh : 1);
   if (load && args.src.kind == TFEM_SRC_NONE) {  // f == 0: still write every row of the load vector
     args.src.kind = TFEM_SRC_CONST;
     args.src.p0 = T(0);
@@ -884,19 +946,22 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
 
 }  // namespace tfem
 
-extern "C" int tfem_tri_p1_assemble_csr_f64(const tfem_tile_plan* host_plan, const double* coords,
-                                            int quad_order, const tfem_bilinear* host_form,
-                                            const tfem_source* host_source, double* csr_val, double* load,
-                                            void* stream) {
-  return tfem::assemble_tiled<double>(host_plan, coords, quad_order, host_form, host_source, csr_val, load, stream);
-}
-
-extern "C" int tfem_tri_p1_assemble_csr_f32(const tfem_tile_plan* host_plan, const float* coords,
-                                            int quad_order, const tfem_bilinear* host_form,
-                                            const tfem_source* host_source, float* csr_val, float* load,
-                                            void* stream) {
-  return tfem::assemble_tiled<float>(host_plan, coords, quad_order, host_form, host_source, csr_val, load, stream);
-}
+#define TFEM_TILED_API(T, SUF)                                                                                        \
+  extern "C" int tfem_tri_p1_assemble_csr_##SUF(const tfem_tile_plan* host_plan, const T* coords, int quad_order,     \
+                                                const tfem_bilinear* host_form, const tfem_source* host_source,       \
+                                                T* csr_val, T* load, void* stream) {                                  \
+    return tfem::assemble_tiled<T>(host_plan, coords, quad_order, host_form, host_source, nullptr, 0, nullptr,        \
+                                   csr_val, load, stream);                                                            \
+  }                                                                                                                   \
+  extern "C" int tfem_tri_p1_assemble_csr_ex_##SUF(const tfem_tile_plan* host_plan, const T* coords, int quad_order,  \
+                                                   const tfem_bilinear* host_form, const tfem_source* host_source,    \
+                                                   const T* f_q, int64_t n_el_per_mesh, const T* frac_metric,         \
+                                                   T* csr_val, T* load, void* stream) {                               \
+    return tfem::assemble_tiled<T>(host_plan, coords, quad_order, host_form, host_source, f_q, n_el_per_mesh,         \
+                                   frac_metric, csr_val, load, stream);                                               \
+  }
+TFEM_TILED_API(double, f64)
+TFEM_TILED_API(float, f32)
 
 #ifdef TFEM_DEBUG_TIMING
 // profiling builds only: cycles per phase summed over all CTAs, [producer | consumer thread 0][8], then zeroed

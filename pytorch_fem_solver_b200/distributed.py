@@ -608,3 +608,68 @@ def _basis_for(mesh, element):
     from . import Basis
 
     return Basis(mesh, element)
+
+
+class PartitionedFractureAssembly:
+    """Element-partitioned assembly of a FRACTURE NETWORK (BASELINE config 5): rank `rank` takes the
+    `rank`-th of `world` contiguous ranges of the flattened element list of `FractureBasis` -- the list behind
+    `global_triangles` (basis/fracture_basis.py:65-69), so a cut may fall inside a fracture or between two -- and
+    assembles it in one launch of the tiled kernel with the fractures' metrics
+    (`tfem_tri_p1_assemble_csr_ex`); rows shared with other ranks (cut lines, trace vertices) are summed at
+    their owner (`InterfacePlan` / `InterfaceExchange`), in fixed rank order.
+
+    `basis` is the whole network's `FractureBasis` on this rank's device: only its index structures and the vertex
+    coordinates are used (set-up); the per-step work touches this rank's elements alone."""
+
+    def __init__(self, basis, rank: int, world: int, group=None, rows_per_tile: int = 336, exchange_ops: Optional[ExchangeOps] = None):
+        import math
+
+        lay = basis._layout
+        if lay.frac is None:
+            raise ValueError("PartitionedFractureAssembly needs a FractureBasis; planar meshes use PartitionedAssembly")
+        device = lay.coords.device
+        n_el, per_mesh = lay.n_total, lay.n_el_per_mesh
+        self.lo, self.hi = (n_el * rank) // world, (n_el * (rank + 1)) // world
+        offsets = (torch.arange(n_el, device=device) // per_mesh) * lay.n_vert_per_mesh
+        geom_conn = (lay.conn.long() + offsets[:, None])[self.lo : self.hi]
+        dof_global = basis._dof_conn_flat().long()[self.lo : self.hi]
+        self.basis, self.rank, self.world = basis, rank, world
+        self.plan = InterfacePlan(dof_global, basis.n_dof_flat, rank, world, group)
+        self.pattern = csr_mod.build_pattern(self.plan.dof_conn, self.plan.n_local, self.plan.extra_keys)
+        self.plan.bind(self.pattern)
+        # rows are clustered fracture by fracture (all fractures share one local 2-D frame)
+        points = torch.zeros((self.plan.n_local, 2), dtype=lay.coords.dtype, device=device)
+        local = lay.coords[geom_conn.reshape(-1)].clone()
+        span = float(lay.coords[:, 0].max() - lay.coords[:, 0].min())  # side by side, no gaps: the blocks stay full
+        fracture_of = torch.div(torch.arange(self.lo, self.hi, device=device), per_mesh, rounding_mode="floor")
+        local[:, 0] += span * fracture_of.repeat_interleave(3).to(local.dtype)
+        points[self.plan.dof_conn.reshape(-1).long()] = local
+        self.tile_plan = csr_mod.build_tile_plan(geom_conn, self.plan.dof_conn, self.pattern, points, rows_per_tile, "block", elem_ids=True)
+        # the kernel finds an element's fracture as (local element id) / n_el_per_mesh: give it a metric table in units of
+        # g = gcd(elements per fracture, first element of the range), in which the range's fracture boundaries are whole rows
+        g = math.gcd(per_mesh, self.lo) if self.lo else per_mesh
+        rows = (self.hi - self.lo + g - 1) // g
+        fracture_of_row = torch.div(self.lo // g + torch.arange(rows, device=device), per_mesh // g, rounding_mode="floor")
+        self.metric = basis._fracture_metric()[fracture_of_row.clamp_max(n_el // per_mesh - 1)].contiguous()
+        self.metric_unit = g
+        self.coords = lay.coords
+        self.quad_order = basis._element.integration_order
+        self.exchange = InterfaceExchange(self.plan, exchange_ops)
+        self.values = torch.empty(self.pattern.nnz, dtype=basis.dtype, device=device)
+        self.load = torch.empty(self.pattern.n_dof, dtype=basis.dtype, device=device)
+
+    def step(self, bilinear=None, source=None):
+        """One distributed assembly: this rank's elements into `self.values` / `self.load` (local CSR of
+        `self.pattern`), then the interface exchange; owned rows (`self.plan.owned_rows`) are complete afterwards."""
+        from . import forms, ops
+
+        src = forms.as_source(source)
+        want_mat, want_vec = bilinear is not None, source is not None
+        f_q = None
+        if want_vec and src.kind == ops.SRC_SAMPLED:
+            f_q = self.basis._sampled_source(src)[self.lo : self.hi].contiguous()
+        alpha, beta = (bilinear.alpha, bilinear.beta) if want_mat else (0.0, 0.0)
+        ops.assemble_csr_tiled(self.tile_plan, self.coords, self.quad_order, alpha, beta, src.kind if want_vec else 0, src.params,
+                               self.values if want_mat else None, self.load if want_vec else None, f_q, self.metric_unit, self.metric)
+        self.exchange(self.values if want_mat else None, self.load if want_vec else None)
+        return (self.values if want_mat else None), (self.load if want_vec else None)

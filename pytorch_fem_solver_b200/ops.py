@@ -310,13 +310,62 @@ def _(coords, conn, n_el_per_mesh, n_vert_per_mesh, quad_order, alpha, beta, wan
     return coords.new_empty((n_el if want_matrix else 0, 3, 3)), coords.new_empty((n_el if source_kind else 0, 3))
 
 
-def assemble_csr_tiled(plan, coords: Tensor, quad_order: int, alpha: float, beta: float, source_kind: int,
-                       source_p, csr_val: Optional[Tensor], load: Optional[Tensor]) -> None:
-    """Thin launcher of tfem_tri_p1_assemble_csr into preallocated outputs (one kernel)."""
-    device = check_cuda(coords, csr_val, load)
+def _tiled_struct(tile_list: Tensor, tile_desc: Tensor, inst_blob: Tensor, tpl_desc: Tensor, tpl_blob: Tensor, meta: List[int],
+                  progress: Optional[Tensor]):
+    """struct tfem_tile_plan from the plan's device arrays and its integer fields (TilePlan.op_args)."""
+    s = _lib.TilePlan()
+    s.n_tiles = int(tile_list.numel())
+    s.tile_list, s.tile_desc, s.inst_blob = tile_list.data_ptr(), tile_desc.data_ptr(), inst_blob.data_ptr()
+    s.tpl_desc, s.tpl_blob = tpl_desc.data_ptr(), tpl_blob.data_ptr()
+    (s.max_vert, s.max_elem, s.max_inst_words, s.max_tb_words, s.max_tc_words, s.has_elem_ids, s.table_bytes,
+     od0, od1, od2, s.consumer_threads, s.reserve_ctas, s.n_progress_tiles) = meta
+    s.od_base[0], s.od_base[1], s.od_base[2] = od0, od1, od2
+    s.progress = None if progress is None else progress.data_ptr()
+    if progress is None:
+        s.n_progress_tiles = 0
+    return s
+
+
+@torch.library.custom_op(f"{NS}::assemble_csr_tiled", mutates_args=("csr_val", "load"))
+def assemble_csr_tiled_op(
+    coords: Tensor, tile_list: Tensor, tile_desc: Tensor, inst_blob: Tensor, tpl_desc: Tensor, tpl_blob: Tensor, meta: List[int],
+    quad_order: int, alpha: float, beta: float, source_kind: int, source_p: List[float], csr_val: Optional[Tensor] = None,
+    load: Optional[Tensor] = None, f_q: Optional[Tensor] = None, n_el_per_mesh: int = 0, frac_metric: Optional[Tensor] = None,
+    progress: Optional[Tensor] = None,
+) -> None:
+    """The fused tiled assembly (tfem_tri_p1_assemble_csr[_ex]) as a registered op: ONE kernel writes the CSR value
+    array and / or the load vector in place.  The tile plan travels as its device arrays plus `meta`
+    (`TilePlan.op_args()`); `f_q` (N, n_q) = source at the quadrature points (source_kind SAMPLED); `frac_metric`
+    (n_mesh, 4) = (a00, a01, a11, det J_f) for fracture networks."""
+    device = check_cuda(coords, tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, csr_val, load, f_q, frac_metric, progress)
+    plan = _tiled_struct(tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, meta, progress)
     form = Bilinear(alpha, beta)
     src = make_source(source_kind, source_p)
-    call("tfem_tri_p1_assemble_csr", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(csr_val), ptr(load))
+    if f_q is None and frac_metric is None:
+        call("tfem_tri_p1_assemble_csr", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(csr_val), ptr(load))
+    else:
+        call("tfem_tri_p1_assemble_csr_ex", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(f_q), n_el_per_mesh,
+             ptr(frac_metric), ptr(csr_val), ptr(load))
+
+
+def assemble_csr_tiled(plan, coords: Tensor, quad_order: int, alpha: float, beta: float, source_kind: int,
+                       source_p, csr_val: Optional[Tensor], load: Optional[Tensor], f_q: Optional[Tensor] = None,
+                       n_el_per_mesh: int = 0, frac_metric: Optional[Tensor] = None) -> None:
+    """Fused tiled assembly into preallocated outputs (one kernel).  `plan`: a `tileplan.TilePlan` (dispatched through
+    the registered op `torch_fem_b200::assemble_csr_tiled`) or its C struct (`TilePlan.c_struct()`: the bare C-ABI call,
+    for per-step hot loops that cannot afford the dispatcher)."""
+    if hasattr(plan, "op_args"):
+        assemble_csr_tiled_op(coords, *plan.op_args(), quad_order, alpha, beta, source_kind, list(source_p), csr_val, load, f_q,
+                              n_el_per_mesh, frac_metric, plan.progress)
+        return
+    device = check_cuda(coords, csr_val, load, f_q, frac_metric)
+    form = Bilinear(alpha, beta)
+    src = make_source(source_kind, source_p)
+    if f_q is None and frac_metric is None:
+        call("tfem_tri_p1_assemble_csr", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(csr_val), ptr(load))
+    else:
+        call("tfem_tri_p1_assemble_csr_ex", coords.dtype, device, plan, ptr(coords), quad_order, form, src, ptr(f_q), n_el_per_mesh,
+             ptr(frac_metric), ptr(csr_val), ptr(load))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -315,6 +315,7 @@ class TilePlan:
     od_base: tuple = (0, 0, 0)  # byte offsets of the three off-diagonal arrays inside the table
     elem_order: int = 1  # 1 = tile elements in ascending id, 2 = even positions first, then odd
     layout_stats: dict = None  # modelled shared-memory wavefronts of the representative tile's reduction phase
+    has_elem_ids: bool = False  # instances carry the global id of every tile element (sampled sources, fractures)
     consumer_threads: int = 0  # compute threads per CTA (256 / 384 / 512); 0 = library default
     tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
     tile_list: torch.Tensor = None  # optional (n,) int32 subset / order of tiles to run (see `subset`)
@@ -331,6 +332,7 @@ class TilePlan:
         s.tpl_desc, s.tpl_blob = self.tpl_desc.data_ptr(), self.tpl_blob.data_ptr()
         s.max_vert, s.max_elem = self.max_vert, self.max_elem
         s.max_inst_words, s.max_tb_words, s.max_tc_words = self.max_inst_words, self.max_tb_words, self.max_tc_words
+        s.has_elem_ids = 1 if self.has_elem_ids else 0
         s.table_bytes = self.table_bytes
         for k in range(3):
             s.od_base[k] = self.od_base[k]
@@ -340,6 +342,14 @@ class TilePlan:
         s.consumer_threads = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads))
         self._keepalive = order  # the struct only holds raw pointers
         return s
+
+    def op_args(self):
+        """(tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, meta) for the registered op `assemble_csr_tiled`."""
+        order = self.default_order if self.tile_list is None else self.tile_list
+        meta = [self.max_vert, self.max_elem, self.max_inst_words, self.max_tb_words, self.max_tc_words, int(self.has_elem_ids),
+                self.table_bytes, *self.od_base, int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)), self.reserve_ctas,
+                self.n_progress_tiles if self.progress is not None else 0]
+        return order, self.tile_desc, self.inst_blob, self.tpl_desc, self.tpl_blob, meta
 
     def subset(self, tile_ids: torch.Tensor, reserve_ctas: int = 0, n_progress_tiles: int = 0, progress: torch.Tensor = None) -> "TilePlan":
         """The same plan restricted to / reordered over some tiles (shares every array); used to
@@ -382,6 +392,8 @@ class TilePlan:
         out["vert"], pos = unpack(inst, pos, out["n_vert"], 32)
         out["seg_start"], pos = unpack(inst, pos, out["n_segs"], 32)
         out["row_id"], pos = unpack(inst, pos, out["n_rows"], 32)
+        if self.has_elem_ids:
+            out["elem_id"], pos = unpack(inst, pos, out["n_elem"], 32)
         assert pos == inst_words
         out["elem"], pos = unpack(tb, TB_HEADER_WORDS, out["n_elem"], 32)
         assert pos == tb_words
@@ -435,12 +447,12 @@ class TileTooLarge(ValueError):
 
 
 def build_tile_plan(geom_conn, dof_conn, pattern, row_points=None, rows_per_tile: int = 336, ordering: str = "auto",
-                    tile_shape: tuple | None = None) -> "TilePlan":
+                    tile_shape: tuple | None = None, elem_ids: bool = False) -> "TilePlan":
     """`_build_tile_plan` with the tile size lowered until every tile fits the kernel's index widths
     (an unstructured mesh has more elements per row than a lattice)."""
     while True:
         try:
-            return _build_tile_plan(geom_conn, dof_conn, pattern, row_points, rows_per_tile, ordering, tile_shape)
+            return _build_tile_plan(geom_conn, dof_conn, pattern, row_points, rows_per_tile, ordering, tile_shape, elem_ids)
         except TileTooLarge:
             if rows_per_tile <= 8:
                 raise
@@ -455,6 +467,7 @@ def _build_tile_plan(
     rows_per_tile: int = 336,
     ordering: str = "auto",
     tile_shape: tuple | None = None,
+    elem_ids: bool = False,
 ) -> TilePlan:
     """Partition CSR rows into tiles and precompute everything the fused kernel gathers.
 
@@ -711,6 +724,9 @@ def _build_tile_plan(
         _Section("seg_start", 32, n_s, seg_tile, seg_local, seg_start),
         _Section("row_id", 32, n_r, row_tile, row_local, row_sorted),
     ]
+    if elem_ids:  # global id of every tile element, in the order of the TB connectivity list: sampled sources
+        # (f at the quadrature points of element e) and per-fracture metrics (fracture = e / elements per fracture)
+        inst_sections.append(_Section("elem_id", 32, n_e, pair_tile, elem_row, pair_elem))
     tb_sections = [
         header([n_v, n_e, n_r, n_s, n_ch, n_h, n_hc], TB_HEADER_WORDS),
         _Section("elem", 32, n_e, pair_tile, elem_row, tile_elem),
@@ -776,4 +792,5 @@ def _build_tile_plan(
         od_base=tuple(od_base),
         elem_order=order,
         layout_stats=layout_stats,
+        has_elem_ids=bool(elem_ids),
     )

@@ -133,19 +133,24 @@ def _source_values(geo, kind, p, f_q):
     return np.zeros(pts.shape[:-1] + (1,))
 
 
-def assemble_csr_tiled(plan_struct, coords, quad_order, alpha, beta, source_kind, source_p, csr_val, load):
+def assemble_csr_tiled(plan_struct, coords, quad_order, alpha, beta, source_kind, source_p, csr_val, load, f_q=None,
+                       n_el_per_mesh=0, frac_metric=None):
+    """The tiled kernel's phases walked on the CPU (tests/plan_emulator.py) over the oracle's local matrices."""
     plan = assemble_csr_tiled.current_plan
     lay = assemble_csr_tiled.current_layout
-    c, k, n_mesh = _batched(lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh)
-    geo = fo.tri_geometry(c, k, quad_order)
+    mat, vec_local = local_forms(lay.coords, lay.conn, lay.n_el_per_mesh, lay.n_vert_per_mesh, quad_order, alpha, beta, True,
+                                 source_kind if load is not None else ops.SRC_CONST, source_p if load is not None else [0.0] * 4,
+                                 f_q, *lay.frac_args())
     n = lay.conn.shape[0]
-    local = fo.quad_reduce(alpha * fo.form_stiffness(geo) + beta * fo.form_mass(geo), geo["dx"]).reshape(n, 3, 3)
-    f = _source_values(geo, source_kind, source_p, None)
-    lvec = fo.quad_reduce(fo.form_load(geo, f), geo["dx"]).reshape(n, 3)
+    if frac_metric is not None:  # the metric handed to the kernel must be J_f^+ J_f^+^T and det J_f
+        inv, det = _np(lay.frac[1]), _np(lay.frac[2])
+        expect = np.stack([(inv @ inv.transpose(0, 2, 1))[:, 0, 0], (inv @ inv.transpose(0, 2, 1))[:, 0, 1],
+                           (inv @ inv.transpose(0, 2, 1))[:, 1, 1], det.reshape(-1)], axis=1)
+        np.testing.assert_allclose(_np(frac_metric), expect, rtol=1e-13, atol=1e-15)
     offsets = (np.arange(n) // lay.n_el_per_mesh) * lay.n_vert_per_mesh
     geom_conn = _np(lay.conn).astype(np.int64) + offsets[:, None]
     nnz, n_dof = assemble_csr_tiled.current_sizes
-    vals, vec = emulate_tiled(plan, None, local, lvec, geom_conn, nnz, n_dof)
+    vals, vec = emulate_tiled(plan, None, _np(mat), _np(vec_local), geom_conn, nnz, n_dof)
     if csr_val is not None:
         csr_val.copy_(torch.from_numpy(vals))
     if load is not None:

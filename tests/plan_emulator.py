@@ -59,6 +59,8 @@ def emulate_tiled(plan, coords, local_mat, local_vec, geom_conn, nnz, n_dof, ord
             m = local_mat[ge]
             table[el + 1] = [m[0, 0], m[1, 1], m[2, 2], m[0, 1], m[1, 2], m[2, 0], *local_vec[ge]]
             global_id[el + 1] = ge
+            if plan.has_elem_ids:
+                assert sec["elem_id"][el] == ge, "elem_id must name the element of the same position in elem[]"
         assert len(set(global_id[1:].tolist())) == n_elem
         assert plan.table_bytes >= max(plan.od_base) + 8 * (plan.max_elem + 2) and all(b % 8 == 0 for b in plan.od_base)
 

@@ -66,7 +66,7 @@ def test_tile_plan_reproduces_oracle(name, mesh, rows_per_tile, ordering):
     n_dof = coords.shape[0]
     tconn = torch.from_numpy(conn)
     pat = csr.build_pattern(tconn, n_dof)
-    plan = csr.build_tile_plan(tconn, tconn, pat, torch.from_numpy(coords), rows_per_tile, ordering)
+    plan = csr.build_tile_plan(tconn, tconn, pat, torch.from_numpy(coords), rows_per_tile, ordering, elem_ids=(rows_per_tile == 16))
     assert plan.halo_factor >= 1.0
     geo = fo.tri_geometry(coords, conn, 3)
     local = fo.quad_reduce(fo.form_stiffness_mass(geo), geo["dx"])
