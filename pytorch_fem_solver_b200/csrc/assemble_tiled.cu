@@ -117,7 +117,9 @@ __device__ __forceinline__ void cp_async(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int THREADS>
 __device__ __forceinline__ void consumer_sync() {
+#ifndef TFEM_DEBUG_NO_BARRIER  // (timing experiment only: results are wrong without the barriers)
   asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+#endif
 }
 
 __host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
@@ -465,7 +467,7 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
       const int n_vert = (int)lds_u32(a_vert);
       const uint32_t a_dst = smem_u32(vxy + stage * args.max_vert);
 #pragma unroll 4
-      for (int i = lane; i < n_vert; i += 32) {
+      for (int i = lane; i < (((TFEM_DEBUG_SKIP & 32) && it >= kStages) ? 0 : n_vert); i += 32) {  // (32: timing experiment, stale coordinates)
         const uint32_t v = lds_u32(a_vert + 4u * (kInstHeader + i));
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(a_dst + (uint32_t)sizeof(V2) * i), "l"(coords2 + v), "n"((int)sizeof(V2)) : "memory");
       }
@@ -501,7 +503,8 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
         const T pbx = args.src.p1 * base.x, pby = args.src.p2 * base.y;
         if (lane < 2) {
           T s, c;
-          sincos_full(lane == 0 ? pbx : pby, s, c);
+          if (TFEM_DEBUG_SKIP & 64) { s = T(0.5); c = T(0.8660254037844386); }  // (64: timing experiment, no library sincos)
+          else sincos_full(lane == 0 ? pbx : pby, s, c);
           T* sb = sbase + 8 * stage;
           if (lane == 0) {
             sb[0] = pbx; sb[1] = pby; sb[2] = s; sb[3] = c;

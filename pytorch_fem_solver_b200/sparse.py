@@ -149,3 +149,64 @@ def cg(
         rel = float(torch.linalg.vector_norm(r)) / b_norm
     converged = rel == rel and rel <= rtol
     return x, CgInfo(iterations, rel, converged)
+
+
+class _CgSolve(torch.autograd.Function):
+    """x = (M A M)^-1 M b through `cg`, differentiable w.r.t. b: for symmetric A the adjoint is one more solve,
+    b_bar = (M A M)^-1 M x_bar (the matrix is a constant of the optimisation, as the Gram matrix of
+    examples/example_weak.py:84-86 is)."""
+
+    @staticmethod
+    def forward(ctx, b, crow, col, val, keep, rtol, max_iterations):
+        x, info = cg(crow, col, val, b.detach(), keep, rtol=rtol, max_iterations=max_iterations)
+        if not info.converged:
+            raise RuntimeError(f"conjugate gradients stopped at relative residual {info.relative_residual:.3e} after {info.iterations} iterations")
+        ctx.save_for_backward(crow, col, val)
+        ctx.keep, ctx.rtol, ctx.max_iterations, ctx.shape = keep, rtol, max_iterations, b.shape
+        ctx.info = info
+        return x.reshape(b.shape)
+
+    @staticmethod
+    def backward(ctx, x_bar):
+        crow, col, val = ctx.saved_tensors
+        if not bool(x_bar.any()):
+            return torch.zeros(ctx.shape, dtype=x_bar.dtype, device=x_bar.device), None, None, None, None, None, None
+        b_bar, info = cg(crow, col, val, x_bar.detach(), ctx.keep, rtol=ctx.rtol, max_iterations=ctx.max_iterations)
+        if not info.converged:
+            raise RuntimeError(f"adjoint conjugate gradients stopped at relative residual {info.relative_residual:.3e}")
+        return b_bar.reshape(ctx.shape), None, None, None, None, None, None
+
+
+def solve(matrix: torch.Tensor, rhs: torch.Tensor, keep: Optional[torch.Tensor] = None, rtol: float = 1e-10,
+          max_iterations: Optional[int] = None) -> torch.Tensor:
+    """`A^-1 rhs` for a symmetric positive definite CSR matrix (rows / columns with keep == 0 masked out), usable inside
+    a loss: gradients flow to `rhs` through a second conjugate-gradient solve."""
+    return _CgSolve.apply(rhs, matrix.crow_indices().to(torch.int32), matrix.col_indices().to(torch.int32), matrix.values(), keep,
+                          rtol, max_iterations)
+
+
+class _QuadraticForm(torch.autograd.Function):
+    """r^T A^-1 r with ONE solve for value and gradient: d/dr = 2 A^-1 r for symmetric A."""
+
+    @staticmethod
+    def forward(ctx, r, crow, col, val, keep, rtol, max_iterations):
+        x, info = cg(crow, col, val, r.detach(), keep, rtol=rtol, max_iterations=max_iterations)
+        if not info.converged:
+            raise RuntimeError(f"conjugate gradients stopped at relative residual {info.relative_residual:.3e} after {info.iterations} iterations")
+        x = x.reshape(r.shape)
+        ctx.save_for_backward(x)
+        masked = r.detach() if keep is None else r.detach() * keep.reshape(r.shape).to(r.dtype)
+        return (masked * x).sum()
+
+    @staticmethod
+    def backward(ctx, loss_bar):
+        (x,) = ctx.saved_tensors
+        return 2.0 * loss_bar * x, None, None, None, None, None, None
+
+
+def inverse_quadratic_form(matrix: torch.Tensor, residual: torch.Tensor, keep: Optional[torch.Tensor] = None, rtol: float = 1e-10,
+                           max_iterations: Optional[int] = None) -> torch.Tensor:
+    """The robust-VPINN loss `r^T G^-1 r` of examples/example_weak.py:84-86,138 on a CSR Gram matrix that cannot be
+    inverted densely: one conjugate-gradient solve gives the value and, since G is symmetric, the gradient 2 G^-1 r."""
+    return _QuadraticForm.apply(residual, matrix.crow_indices().to(torch.int32), matrix.col_indices().to(torch.int32), matrix.values(),
+                                keep, rtol, max_iterations)

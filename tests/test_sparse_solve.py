@@ -113,6 +113,48 @@ def test_cg_stops_on_breakdown_and_respects_limits():
         mp.undo()
 
 
+def _rvpinn_loss_check(device):
+    """r^T G^-1 r and A^-1 b inside a loss: values and gradients against the dense formulas (example_weak.py:84-86,138)."""
+    rng = np.random.default_rng(2)
+    n = 60
+    m = scipy.sparse.random(n, n, density=0.1, random_state=3, format="csr")
+    a = (m @ m.T + n * scipy.sparse.identity(n)).tocsr()
+    a.sort_indices()
+    dense = torch.tensor(a.toarray(), device=device)
+    matrix = torch.sparse_csr_tensor(torch.from_numpy(a.indptr.astype(np.int32)), torch.from_numpy(a.indices.astype(np.int32)),
+                                     torch.from_numpy(a.data), size=(n, n)).to(device)
+    keep = torch.ones(n, dtype=torch.uint8, device=device)
+    keep[[0, 5, n - 1]] = 0
+    idx = torch.nonzero(keep, as_tuple=True)[0]
+    theta = torch.tensor(rng.standard_normal(n), device=device, requires_grad=True)
+    r = torch.sin(theta) + 0.3 * theta  # any differentiable producer of the residual
+    loss = sparse.inverse_quadratic_form(matrix, r.reshape(-1, 1), keep, rtol=1e-13)
+    (g,) = torch.autograd.grad(loss, theta, retain_graph=True)
+    theta_ref = theta.detach().clone().requires_grad_(True)
+    r_ref = (torch.sin(theta_ref) + 0.3 * theta_ref)[idx]
+    loss_ref = r_ref @ torch.linalg.solve(dense[idx][:, idx], r_ref)
+    (g_ref,) = torch.autograd.grad(loss_ref, theta_ref, retain_graph=True)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-10 * abs(float(loss_ref))
+    assert float((g - g_ref).abs().max()) <= 1e-9 * float(g_ref.abs().max())
+    x = sparse.solve(matrix, r.reshape(-1, 1), keep, rtol=1e-13)
+    w = torch.tensor(rng.standard_normal(n), device=device)
+    (g2,) = torch.autograd.grad((x.reshape(-1) * w).sum(), theta)
+    x_ref = torch.zeros(n, dtype=torch.float64, device=device)
+    x_ref[idx] = torch.linalg.solve(dense[idx][:, idx], (torch.sin(theta_ref) + 0.3 * theta_ref)[idx])
+    (g2_ref,) = torch.autograd.grad((x_ref * w).sum(), theta_ref)
+    assert float((g2 - g2_ref).abs().max()) <= 1e-9 * float(g2_ref.abs().max())
+
+
+def test_rvpinn_loss_is_differentiable_host_logic(monkeypatch):
+    cpu_shim.install(monkeypatch)
+    _rvpinn_loss_check("cpu")
+
+
+@pytest.mark.gpu
+def test_rvpinn_loss_is_differentiable_gpu():
+    _rvpinn_loss_check("cuda")
+
+
 def test_solve_csr_path_host_logic(monkeypatch):
     cpu_shim.install(monkeypatch)
     check_solve("cpu", 24, 20, monkeypatch)
