@@ -124,3 +124,49 @@ def test_one_fracture_equals_planar_gpu():
 @pytest.mark.gpu
 def test_one_patch_equals_basis_gpu():
     one_patch_equals_basis("cuda")
+
+
+def test_refine_patches_children_tile_their_parent():
+    """mesh/patches.py:49-149.  The reference's refine_patches raises on its own data (it reshapes the children's
+    5-vertex blocks to (-1, 4, 2)), so the port is pinned by what the routine is meant to produce: four children of
+    half the radius centred on the parent's quadrant centres, one patch of radius sqrt(2)/2 r rotated by 45 degrees
+    about the parent's centre, old patches dropped or kept, and vertex blocks that are exactly the patches
+    `Patches(centers, radius)` would build."""
+    import math
+
+    from pytorch_fem_solver_b200 import meshgen
+    from pytorch_fem_solver_b200.mesh.patches import Patches
+
+    centers, radius = meshgen.generate_patches_info(2)
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        _check_refinement(Patches, centers, radius, math)
+    finally:
+        torch.set_default_dtype(previous)
+
+
+def _check_refinement(Patches, centers, radius, math):
+    patches = Patches(torch.tensor(centers), torch.tensor(radius))
+    marks = torch.zeros(16, dtype=torch.bool)
+    marks[[1, 4, 5, 11]] = True
+    for keep_old in (False, True):
+        c, r, v = patches.refine_patches(marks, maintain_old_patches=keep_old)
+        n_old = 16 if keep_old else 12
+        assert c.shape == (n_old + 20, 2) and r.shape == (n_old + 20, 1) and v.shape == (n_old + 20, 5, 2)
+        rebuilt = Patches(c[: n_old + 16], r[: n_old + 16])["vertices", "coordinates"]
+        assert torch.allclose(v[: n_old + 16], rebuilt, rtol=0, atol=1e-15)  # kept patches and axis-aligned children
+        parents_c, parents_r = torch.tensor(centers)[marks], torch.tensor(radius)[marks]
+        children_c = c[n_old : n_old + 16].reshape(4, 4, 2)
+        assert torch.allclose(children_c.mean(1), parents_c)  # the four children surround the parent's centre
+        assert torch.allclose(r[n_old : n_old + 16], (0.5 * parents_r).repeat(4, 1))
+        area = lambda rr: (2 * rr) ** 2  # noqa: E731
+        assert torch.allclose(4 * area(r[n_old : n_old + 4]), area(parents_r))  # children tile the parent
+        rot_c, rot_r, rot_v = c[n_old + 16 :], r[n_old + 16 :], v[n_old + 16 :]
+        assert torch.equal(rot_c, parents_c) and torch.allclose(rot_r, parents_r / math.sqrt(2.0))
+        assert torch.allclose(rot_v[:, 4], parents_c)  # centre vertex last
+        corner = rot_v[:, :4] - parents_c.unsqueeze(1)
+        assert torch.allclose(corner.norm(dim=-1), (math.sqrt(2.0) * rot_r).expand(-1, 4))  # a square of half-diagonal sqrt(2) r'
+        assert torch.allclose(corner.abs().min(dim=-1).values, torch.zeros(4, 4, dtype=corner.dtype), atol=1e-15)  # corners on the axes
+    c, r, v = patches.uniform_refine(1)
+    assert c.shape[0] == 16 * 5 and torch.allclose(r[:64], torch.full((64, 1), 0.0625, dtype=r.dtype))
