@@ -154,8 +154,8 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm runs on rank 0 alone and may
     # use every host core
     torch.set_num_threads(len(os.sched_getaffinity(0)))
-    # bounded sample of the same workload: a quarter-height strip keeps a step near one second
-    nx, ny = args.nx, max(args.ny // 4, 1)
+    # the full workload of the repo arm: one step = the whole nx x ny mesh (about two seconds on 16 host cores)
+    nx, ny = args.nx, args.ny
     from oracle.torch_cpu_port import reference_assembly_cpu
     from pytorch_fem_solver_b200 import meshgen
 
@@ -170,7 +170,7 @@ def run_reference(args):
     elapsed = time.perf_counter() - t0
     value = n_el * args.steps / elapsed
     cores = torch.get_num_threads()
-    sample = f"{n_el} of {2 * args.nx * args.ny} elements per step (nx={nx}, ny={ny})"
+    sample = f"all {n_el} elements per step (nx={nx}, ny={ny}); {args.warmup} warm-up + {args.steps} timed steps"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -428,9 +428,11 @@ def run_ours(args):
                 "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": ncu_traffic(args),
+                "traffic_source": "static: one `ncu --set full` capture of this kernel on this configuration, committed as "
+                "profiles/roofline_traffic.json (not re-measured in this run; DRAM writes still in L2 at kernel end are not in it)",
                 "peak_source": peak_source,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
-                "kernel": "assemble_tiled_kernel<double,384,3,SINSIN,true>" if args.path == "tiled" else "local_forms + segment_reduce x2",
+                "kernel": "assemble_tiled_kernel<double,384,3,SINSIN,true,false>" if args.path == "tiled" else "local_forms + segment_reduce x2",
                 "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": algorithmic,
                 "bytes_per_element": algorithmic / n_el,

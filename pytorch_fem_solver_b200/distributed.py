@@ -489,13 +489,17 @@ class PartitionedAssembly:
         stream = torch.cuda.Stream(device=self.buffer.device)
         graphs = []
         try:
+            from . import _lib
+
             for parity in (0, 1):
                 assert exchange.steps & 1 == parity
+                launches_before = sum(_lib.LAUNCHES.values())
                 graph = torch.cuda.CUDAGraph()
                 stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
                     self._single_launch_step(torch.cuda.current_stream(), alpha, beta, None, self.buffer, captured=True)
                 graphs.append(graph)
+                self._graph_kernels = sum(_lib.LAUNCHES.values()) - launches_before  # our kernels inside one replay
                 graph.replay()  # the recorded step has not run yet: run it, every rank the same parity
                 torch.cuda.synchronize()
         except Exception as error:  # noqa: BLE001 - reported; the eager step keeps working
@@ -511,9 +515,12 @@ class PartitionedAssembly:
         """One distributed assembly through the captured graphs (after `capture()`), else a plain `step()`."""
         if getattr(self, "_graphs", None) is None:
             return self.step()
+        from . import _lib
+
         self._graphs[self._graph_parity].replay()
         self._graph_parity ^= 1
         self.fused_exchange.steps += 1
+        _lib.LAUNCHES["graph_replay"] = _lib.LAUNCHES.get("graph_replay", 0) + self._graph_kernels
 
     def step(self, alpha: float = 1.0, beta: float = 1.0, coords: Optional[torch.Tensor] = None,
              buffer: Optional[torch.Tensor] = None):
