@@ -219,6 +219,15 @@ int tfem_sm_count(void);
                                      const T* frac_jac, const T* frac_inv, const T* frac_det,      \
                                      const T* frac_t, const tfem_source* host_source,              \
                                      const T* f_q, const T* grad_u, T* local_vec, void* stream);   \
+  /* The same residual summed straight to the DOF vector r [n_dof] in ONE launch of the tiled      \
+   * kernel (no per-element tensor, no scatter pass; rows sum their elements in increasing         \
+   * element order): f_q [n_el,n_q] or NULL (f = 0), grad_u [n_el,n_q,d]; on a fracture network    \
+   * frac_inv [n_mesh,2,3] = J_f^+ and frac_metric [n_mesh,4] as in assemble_csr_ex (d = 3), both  \
+   * NULL on planar meshes (d = 2).  The plan must carry element ids (has_elem_ids). */            \
+  int tfem_weak_residual_tiled_##SUF(const tfem_tile_plan* host_plan, const T* coords,             \
+                                     int quad_order, const T* f_q, const T* grad_u,                \
+                                     int64_t n_el_per_mesh, const T* frac_inv,                     \
+                                     const T* frac_metric, T* r, void* stream);                    \
   /* Adjoint of the above w.r.t. grad_u (what autograd derives from index_put_/sum/matmul):       \
    * grad_u_bar[e,q,:] = -dx[e,q] * sum_i grad phi_i[e,:] * r_bar[dof_conn[e,i]]. */              \
   int tfem_weak_residual_bwd_##SUF(int64_t n_el, int64_t n_el_per_mesh, int64_t n_vert_per_mesh,   \

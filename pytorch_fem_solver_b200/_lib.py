@@ -77,6 +77,7 @@ _TYPED = {
     "tfem_tri_p1_assemble_csr": [POINTER(TilePlan), P, c_int, POINTER(Bilinear), POINTER(Source), P, P, P],
     "tfem_tri_p1_assemble_csr_ex": [POINTER(TilePlan), P, c_int, POINTER(Bilinear), POINTER(Source), P, I64, P, P, P, P],
     "tfem_weak_residual_local": [I64, I64, I64, P, P, c_int, P, P, P, P, POINTER(Source), P, P, P, P],
+    "tfem_weak_residual_tiled": [POINTER(TilePlan), P, c_int, P, P, I64, P, P, P, P],
     "tfem_weak_residual_bwd": [I64, I64, I64, P, P, P, c_int, P, P, P, P, P, P],
     "tfem_batched_weak_residual": [I64, c_int, c_int, P, P, c_int, POINTER(Source), P, P, P, P],
     "tfem_h1_error": [I64, I64, I64, P, P, c_int, P, c_int, P, P, P, P, P, P],

@@ -174,6 +174,20 @@ class AbstractBasis(abc.ABC):
                                                             elem_ids=bool(elem_ids))
         return self._tile_plans[key]
 
+    #: weak-residual path: "auto" = the one-launch tiled kernel from RESIDUAL_TILED_MIN elements on (below, the tile
+    #: plan's set-up outweighs the saved pass), "tiled" / "two_pass" force one (tests, benchmarks)
+    residual_path = "auto"
+    RESIDUAL_TILED_MIN = 1 << 16
+
+    def _residual_tiled(self, src) -> bool:
+        lay = self._layout
+        supported = src.kind in (ops.SRC_SAMPLED, ops.SRC_NONE) and getattr(self, "_tiled_residual_ok", True)
+        if self.residual_path == "tiled":
+            if not supported:
+                raise NotImplementedError("the tiled weak residual takes a sampled source (or none) on Basis / FractureBasis")
+            return True
+        return self.residual_path == "auto" and supported and lay.n_total >= self.RESIDUAL_TILED_MIN
+
     def _fracture_metric(self) -> Optional[torch.Tensor]:
         """(n_mesh, 4) = (a00, a01, a11, det J_f) with a = J_f^+ J_f^+^T: the metric in which the planar element
         vectors give the tangential gradients' inner products (fracture_basis.py:20-26)."""
@@ -272,11 +286,20 @@ class AbstractBasis(abc.ABC):
             src = function.source
             grad = forms.WeakResidual.field(self, args[0])
             f_q = self._sampled_source(src) if src.kind == ops.SRC_SAMPLED else None
-            vec = ops.weak_residual(
-                grad.to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous(), lay.coords, lay.conn,
-                self._dof_conn_flat(), pat.lin_seg, pat.lin_perm, lay.n_el_per_mesh, lay.n_vert_per_mesh,
-                self._element.integration_order, src.kind, list(src.params), f_q, *lay.frac_args(),
-            )
+            grad_q = grad.to(self.dtype).expand(*lay.lead, self.n_q, 1, lay.d).reshape(lay.n_total, self.n_q, lay.d).contiguous()
+            if self._residual_tiled(src):
+                # one launch of the tiled kernel: rows sum their elements' terms, no (N,3) tensor, no scatter pass
+                plan = self.tile_plan(elem_ids=True)
+                frac_jac, frac_inv, frac_det, _ = lay.frac_args()
+                vec = ops.weak_residual_tiled(
+                    grad_q, lay.coords, lay.conn, self._dof_conn_flat(), *plan.op_args(), pat.n_dof, lay.n_el_per_mesh,
+                    lay.n_vert_per_mesh, self._element.integration_order, f_q, frac_jac, frac_inv, frac_det, self._fracture_metric(),
+                )
+            else:
+                vec = ops.weak_residual(
+                    grad_q, lay.coords, lay.conn, self._dof_conn_flat(), pat.lin_seg, pat.lin_perm, lay.n_el_per_mesh,
+                    lay.n_vert_per_mesh, self._element.integration_order, src.kind, list(src.params), f_q, *lay.frac_args(),
+                )
         elif isinstance(function, forms.Load) and not args and not kwargs:
             vec = self._assemble_fused(None, function.source)[1]
         else:

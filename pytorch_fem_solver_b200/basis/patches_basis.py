@@ -10,6 +10,8 @@ from .abstract_basis import AbstractBasis, CellLayout, LazyParameters
 class PatchesBasis(AbstractBasis):
     """Every mesh of the batch is its own little FE space; nothing couples patches."""
 
+    _tiled_residual_ok = False  # patches have their own one-launch kernel (tfem_batched_weak_residual)
+
     def __init__(self, mesh, element):
         self.nb_patches = mesh.batch_size()[0]
         super().__init__(mesh, element)

@@ -171,6 +171,8 @@ __device__ __forceinline__ void sts_1(uint32_t a, float x) { asm volatile("st.sh
 template <typename T>
 __device__ __forceinline__ uint32_t code_offset(uint32_t code) { return sizeof(T) == 8 ? code : code >> 1; }
 
+constexpr int kSrcResidual = 100;  // internal source kind of tfem_weak_residual_tiled (not part of tfem_source_kind)
+
 template <int ORDER> struct NQ;
 template <> struct NQ<1> { static constexpr int value = 1; };
 template <> struct NQ<2> { static constexpr int value = 3; };
@@ -222,6 +224,7 @@ struct TiledConst {
   T kcw, md, mo;                // alpha * sum_q w_q ; beta * reference mass (diagonal, off-diagonal)
   T c1[kMaxQ], c2q[kMaxQ];      // barycentric offsets of the quadrature points from the centroid
   T wl0[kMaxQ], wl1[kMaxQ], wl2[kMaxQ];  // w_q * l_i(q)
+  T wq[kMaxQ];                           // w_q
   T m0, m1, m2;                 // sum_q w_q l_i(q)  (constant source)
   T o3_w1, o3_w2;               // 4-point rule: source frequencies * 2/15 (offsets of its outer points from the centroid)
   T o3_a, o3_b, o3_c;           // 4-point rule: w_c / 3, w_o / 5, 2 w_o / 5
@@ -246,6 +249,7 @@ TiledConst<T> make_tiled_const(int order, const QuadT<T>& quad, T alpha, T beta,
     c.c1[q] = T(l1 - 1.0 / 3.0);
     c.c2q[q] = T(l2 - 1.0 / 3.0);
     c.wl0[q] = T(w * l0); c.wl1[q] = T(w * l1); c.wl2[q] = T(w * l2);
+    c.wq[q] = T(w);
     m0 += w * l0; m1 += w * l1; m2 += w * l2;
   }
   c.m0 = T(m0); c.m1 = T(m1); c.m2 = T(m2);
@@ -364,6 +368,8 @@ struct TiledArgs {
   uint32_t* progress;
   const T* coords;
   const T* f_q;          // [n_el, n_q] source at the quadrature points (TFEM_SRC_SAMPLED), via the instances' elem_id section
+  const T* grad_u;       // [n_el, n_q, d] (weak residual): grad u at the quadrature points, d = 3 on fractures else 2
+  const T* frac_inv;     // [n_mesh, 2, 3] J_f^+ (weak residual on fractures)
   const T* frac_metric;  // [n_mesh, 4] (a00, a01, a11, det J_f) or NULL; element e lies on fracture e / n_el_per_mesh
   int n_el_per_mesh;
   SourceT<T> src;
@@ -386,7 +392,8 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
   constexpr bool HAS_LOAD = SRC != TFEM_SRC_NONE;
   constexpr bool SINSIN = SRC == TFEM_SRC_SINSIN;
   constexpr bool SAMPLED = SRC == TFEM_SRC_SAMPLED;
-  constexpr bool NEED_IDS = SAMPLED || FRAC;
+  constexpr bool RESIDUAL = SRC == kSrcResidual;  // weak residual: f v - grad v . grad u, both given at the quadrature points
+  constexpr bool NEED_IDS = SAMPLED || FRAC || RESIDUAL;
   constexpr int kWarps = CONSUMERS / 32;
   constexpr uint32_t kRowBytes = kDlSlots * sizeof(T);
   constexpr uint32_t kS = sizeof(T);
@@ -580,12 +587,35 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
       const uint32_t out = a_tab + row * kRowBytes;
       // sampled source / fracture metric of this element, fetched first so the loads overlap the geometry
       T fq[NQV];
+      T ru0 = T(0), ru1 = T(0), ru2 = T(0);
       T a00 = T(1), a01 = T(0), a11 = T(1), detf = T(1);
+      (void)ru2;
       if constexpr (NEED_IDS) {
         const int64_t eid = (int64_t)lds_u32(a_eid + 4u * slot);
         if constexpr (SAMPLED) {
 #pragma unroll
           for (int q = 0; q < NQV; ++q) fq[q] = __ldg(args.f_q + eid * NQV + q);
+        }
+        if constexpr (RESIDUAL) {
+          // U = sum_q w_q grad u(x_q) (the basis gradients are constant on the element) and the samples of f
+          constexpr int D = FRAC ? 3 : 2;
+          const T* gu = args.grad_u + eid * (NQV * D);
+          ru0 = ru1 = ru2 = T(0);
+#pragma unroll
+          for (int q = 0; q < NQV; ++q) {
+            const T w = cst.wq[q];
+            ru0 = fma(w, __ldg(gu + q * D), ru0);
+            ru1 = fma(w, __ldg(gu + q * D + 1), ru1);
+            if constexpr (FRAC) ru2 = fma(w, __ldg(gu + q * D + 2), ru2);
+            fq[q] = args.f_q ? __ldg(args.f_q + eid * NQV + q) : T(0);
+          }
+          if constexpr (FRAC) {  // pull the 3-D vector back to the fracture's plane: J_f^+ U
+            const T* ji = args.frac_inv + 6 * (eid / args.n_el_per_mesh);
+            const T p0 = fma(__ldg(ji), ru0, fma(__ldg(ji + 1), ru1, __ldg(ji + 2) * ru2));
+            const T p1 = fma(__ldg(ji + 3), ru0, fma(__ldg(ji + 4), ru1, __ldg(ji + 5) * ru2));
+            ru0 = p0;
+            ru1 = p1;
+          }
         }
         if constexpr (FRAC) {
           const T* metric = args.frac_metric + 4 * (eid / args.n_el_per_mesh);
@@ -688,6 +718,18 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
               }
             }
           }
+        } else if constexpr (RESIDUAL) {
+          // r_i = det_f (det sum_q w_q l_i f_q  -  e_i . U),  grad phi_i = e_i / det, e_1 = (by, -bx), e_2 = (-ay, ax)
+#pragma unroll
+          for (int q = 0; q < NQV; ++q) {
+            b0 = fma(cst.wl0[q], fq[q], b0);
+            b1 = fma(cst.wl1[q], fq[q], b1);
+            b2 = fma(cst.wl2[q], fq[q], b2);
+          }
+          const T e1u = fma(by, ru0, -(bx * ru1)), e2u = fma(ax, ru1, -(ay * ru0));
+          b0 = fma(det, b0, e1u + e2u);
+          b1 = fma(det, b1, -e1u);
+          b2 = fma(det, b2, -e2u);
         } else if constexpr (SAMPLED) {  // f given at the element's quadrature points
 #pragma unroll
           for (int q = 0; q < NQV; ++q) {
@@ -698,7 +740,7 @@ assemble_tiled_kernel(const TiledArgs<T> args, const TiledConst<T> cst, const Qu
         } else {  // constant source: the moments of the basis functions are constants
           b0 = cst.m0; b1 = cst.m1; b2 = cst.m2;
         }
-        const T amp = (SAMPLED ? T(1) : args.src.p0) * (FRAC ? det * detf : det);
+        const T amp = RESIDUAL ? detf : (SAMPLED ? T(1) : args.src.p0) * (FRAC ? det * detf : det);
         b0 *= amp; b1 *= amp; b2 *= amp;
       }
       sts_2(out, k00, b0);
@@ -845,7 +887,7 @@ int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledCons
   }
   return TFEM_ERR_UNSUPPORTED;
 #else
-  if (args.frac_metric) {  // fracture network: tangential forms; analytic sources live in 3-D and come sampled
+  if (args.frac_metric && kind != kSrcResidual) {  // fracture network: tangential forms; analytic sources live in 3-D and come sampled
     if (args.csr_val) {
       if (kind == TFEM_SRC_SAMPLED) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, true, true>(hp, args, cst, quad, s);
       if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, true, true>(hp, args, cst, quad, s);
@@ -855,6 +897,10 @@ int dispatch_tiled(const tfem_tile_plan* hp, TiledArgs<T>& args, const TiledCons
     if (kind == TFEM_SRC_SAMPLED) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, false, true>(hp, args, cst, quad, s);
     if (kind == TFEM_SRC_CONST) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_CONST, false, true>(hp, args, cst, quad, s);
     return TFEM_ERR_UNSUPPORTED;
+  }
+  if (kind == kSrcResidual) {
+    if (args.frac_metric) return launch_tiled<T, CONSUMERS, ORDER, kSrcResidual, false, true>(hp, args, cst, quad, s);
+    return launch_tiled<T, CONSUMERS, ORDER, kSrcResidual, false, false>(hp, args, cst, quad, s);
   }
   if (kind == TFEM_SRC_SAMPLED) {
     if (args.csr_val) return launch_tiled<T, CONSUMERS, ORDER, TFEM_SRC_SAMPLED, true>(hp, args, cst, quad, s);
@@ -949,7 +995,61 @@ int assemble_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, co
 
 }  // namespace tfem
 
+namespace tfem {
+// Weak residual r = sum over elements of  sum_q dx (f phi_i - grad phi_i . grad u)  straight to the DOF vector in ONE launch
+// of the tiled kernel (load-vector path: rows sum their elements' terms in increasing element order).
+template <typename T>
+int weak_residual_tiled(const tfem_tile_plan* hp, const T* coords, int quad_order, const T* f_q, const T* grad_u,
+                        int64_t n_el_per_mesh, const T* frac_inv, const T* frac_metric, T* r, void* stream) {
+  if (!hp || hp->n_tiles < 0) return TFEM_ERR_BAD_ARG;
+  if (hp->n_tiles == 0) return TFEM_OK;
+  if (!coords || !grad_u || !r || !hp->has_elem_ids) return TFEM_ERR_BAD_ARG;
+  if ((frac_inv == nullptr) != (frac_metric == nullptr)) return TFEM_ERR_BAD_ARG;
+  if (frac_inv && n_el_per_mesh <= 0) return TFEM_ERR_BAD_ARG;
+  if (!hp->tile_list || !hp->tile_desc || !hp->inst_blob || !hp->tpl_desc || !hp->tpl_blob) return TFEM_ERR_BAD_ARG;
+  if (hp->max_vert > 1024 || hp->max_elem > 880 || hp->table_bytes > 65536 || hp->table_bytes % 16 != 0) return TFEM_ERR_TOO_LARGE;
+  if (tri_n_q(quad_order) == 0) return TFEM_ERR_UNSUPPORTED;
+  TiledArgs<T> args{};
+  args.src.kind = kSrcResidual;
+  args.src.p0 = T(1);
+  const QuadT<T> quad = make_quad<T>(quad_order);
+  args.n_tiles = (int)hp->n_tiles;
+  args.n_strided = 0;
+  args.progress = nullptr;
+  args.tile_list = hp->tile_list;
+  args.tile_desc = reinterpret_cast<const int4*>(hp->tile_desc);
+  args.inst_blob = hp->inst_blob;
+  args.tpl_desc = reinterpret_cast<const int4*>(hp->tpl_desc);
+  args.tpl_blob = hp->tpl_blob;
+  args.max_vert = hp->max_vert;
+  args.max_elem = hp->max_elem;
+  for (int k = 0; k < 3; ++k) args.od_base[k] = hp->od_base[k] / 8 * (int)sizeof(T);
+  args.coords = coords;
+  args.f_q = f_q;
+  args.grad_u = grad_u;
+  args.frac_inv = frac_inv;
+  args.frac_metric = frac_metric;
+  args.n_el_per_mesh = (int)(n_el_per_mesh > 0 ? n_el_per_mesh : 1);
+  const TiledConst<T> cst = make_tiled_const<T>(quad_order, quad, T(0), T(0), args.src);
+  args.csr_val = nullptr;
+  args.load = r;
+  auto s = static_cast<cudaStream_t>(stream);
+  switch (quad_order) {
+    case 1: return dispatch_tiled<T, 384, 1>(hp, args, cst, quad, s);
+    case 2: return dispatch_tiled<T, 384, 2>(hp, args, cst, quad, s);
+    case 3: return dispatch_tiled<T, 384, 3>(hp, args, cst, quad, s);
+    default: return dispatch_tiled<T, 384, 4>(hp, args, cst, quad, s);
+  }
+}
+}  // namespace tfem
+
 #define TFEM_TILED_API(T, SUF)                                                                                        \
+  extern "C" int tfem_weak_residual_tiled_##SUF(const tfem_tile_plan* host_plan, const T* coords, int quad_order,     \
+                                                const T* f_q, const T* grad_u, int64_t n_el_per_mesh,                 \
+                                                const T* frac_inv, const T* frac_metric, T* r, void* stream) {        \
+    return tfem::weak_residual_tiled<T>(host_plan, coords, quad_order, f_q, grad_u, n_el_per_mesh, frac_inv,          \
+                                        frac_metric, r, stream);                                                      \
+  }                                                                                                                   \
   extern "C" int tfem_tri_p1_assemble_csr_##SUF(const tfem_tile_plan* host_plan, const T* coords, int quad_order,     \
                                                 const tfem_bilinear* host_form, const tfem_source* host_source,       \
                                                 T* csr_val, T* load, void* stream) {                                  \

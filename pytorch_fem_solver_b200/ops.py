@@ -520,6 +520,54 @@ def _weak_residual_backward(ctx, r_bar):
 weak_residual.register_autograd(_weak_residual_backward, setup_context=_weak_residual_setup)
 
 
+@torch.library.custom_op(f"{NS}::weak_residual_tiled", mutates_args=())
+def weak_residual_tiled(
+    grad_u: Tensor, coords: Tensor, conn: Tensor, dof_conn: Tensor, tile_list: Tensor, tile_desc: Tensor, inst_blob: Tensor,
+    tpl_desc: Tensor, tpl_blob: Tensor, meta: List[int], n_dof: int, n_el_per_mesh: int, n_vert_per_mesh: int, quad_order: int,
+    f_q: Optional[Tensor] = None, frac_jac: Optional[Tensor] = None, frac_inv: Optional[Tensor] = None,
+    frac_det: Optional[Tensor] = None, frac_metric: Optional[Tensor] = None,
+) -> Tensor:
+    """Global weak residual r (n_dof,) in ONE launch of the tiled kernel (`tfem_weak_residual_tiled`): no per-element
+    tensor, no scatter pass.  The tile plan (built with element ids) travels as its device arrays plus `meta`; `f_q`
+    (N, n_q) = f at the quadrature points or None (f = 0); fracture networks pass J_f^+ (`frac_inv`) and the plane
+    metric (`frac_metric`).  `conn`, `dof_conn`, `frac_jac`, `frac_det` only serve the adjoint (`weak_residual_bwd`)."""
+    device = check_cuda(grad_u, coords, tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, f_q, frac_inv, frac_metric)
+    n_q = _nq_tri(quad_order)
+    d = 3 if frac_inv is not None else 2
+    if tuple(grad_u.shape) != (conn.shape[0], n_q, d):
+        raise TfemError(f"grad_u must have shape {(conn.shape[0], n_q, d)}, got {tuple(grad_u.shape)}")
+    plan = _tiled_struct(tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, meta, None)
+    out = torch.empty((n_dof,), dtype=coords.dtype, device=device)
+    call("tfem_weak_residual_tiled", coords.dtype, device, plan, ptr(coords), quad_order, ptr(f_q), ptr(grad_u), n_el_per_mesh,
+         ptr(frac_inv), ptr(frac_metric), ptr(out))
+    return out
+
+
+@weak_residual_tiled.register_fake
+def _(grad_u, coords, conn, dof_conn, tile_list, tile_desc, inst_blob, tpl_desc, tpl_blob, meta, n_dof, n_el_per_mesh,
+      n_vert_per_mesh, quad_order, f_q=None, frac_jac=None, frac_inv=None, frac_det=None, frac_metric=None):
+    return coords.new_empty((n_dof,))
+
+
+def _weak_residual_tiled_setup(ctx, inputs, output):
+    (grad_u, coords, conn, dof_conn, _tl, _td, _ib, _pd, _pb, _meta, _n_dof, n_el_per_mesh, n_vert_per_mesh, quad_order,
+     _f_q, frac_jac, frac_inv, frac_det, _metric) = inputs
+    ctx.save_for_backward(coords, conn, dof_conn, frac_jac, frac_inv, frac_det)
+    ctx.meta = (n_el_per_mesh, n_vert_per_mesh, quad_order)
+
+
+def _weak_residual_tiled_backward(ctx, r_bar):
+    coords, conn, dof_conn, frac_jac, frac_inv, frac_det = ctx.saved_tensors
+    n_el_per_mesh, n_vert_per_mesh, quad_order = ctx.meta
+    grad = weak_residual_bwd(
+        r_bar.contiguous(), coords, conn, dof_conn, n_el_per_mesh, n_vert_per_mesh, quad_order, frac_jac, frac_inv, frac_det
+    )
+    return (grad,) + (None,) * 18
+
+
+weak_residual_tiled.register_autograd(_weak_residual_tiled_backward, setup_context=_weak_residual_tiled_setup)
+
+
 @torch.library.custom_op(f"{NS}::h1_error", mutates_args=())
 def h1_error(u: Tensor, grad_u: Tensor, u_ex: Tensor, grad_ex: Tensor, coords: Tensor, conn: Tensor, n_el_per_mesh: int,
              n_vert_per_mesh: int, quad_order: int, frac_det: Optional[Tensor] = None) -> Tensor:

@@ -158,6 +158,11 @@ def test_config4_full_size_weak_residual_and_adjoint():
     f_q = api_checks.rhs3_np(geo["integration_points"])
     ref = fo.scatter_linear(fo.quad_reduce(fo.form_weak_residual(geo, f_q, grad), geo["dx"]), tris, n_g)
     gu = torch.tensor(grad, device=DEV, requires_grad=True)
+    basis.residual_path = "two_pass"  # element kernel + scatter
+    r2 = basis.integrate_linear_form(forms.WeakResidual(api_checks.rhs3), gu.detach())
+    assert relmax(r2.cpu().numpy().reshape(-1), ref.reshape(-1)) < 1e-12
+    basis.residual_path = "auto"  # at this size: one launch of the tiled kernel
+    assert basis._residual_tiled(forms.as_source(api_checks.rhs3))
     r = basis.integrate_linear_form(forms.WeakResidual(api_checks.rhs3), gu)
     assert relmax(r.detach().cpu().numpy().reshape(-1), ref.reshape(-1)) < 1e-12
     cot = rng.standard_normal(ref.shape)

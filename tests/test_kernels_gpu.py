@@ -9,6 +9,7 @@ import torch
 import pytorch_fem_solver_b200 as tfem
 from oracle import fem_oracle as fo
 from pytorch_fem_solver_b200 import forms, meshgen
+from tests import api_checks
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -159,6 +160,63 @@ def test_weak_residual_large_against_oracle():
     (r * torch.tensor(cot, device=DEV)).sum().backward()
     ref_bar = fo.weak_residual_backward(geo, conn, cot)
     assert relmax(gu.grad.cpu().numpy(), ref_bar) < 1e-12
+
+
+@pytest.mark.parametrize("order", [2, 3, 4])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_weak_residual_tiled_one_launch(order, dtype):
+    """`tfem_weak_residual_tiled` (rows sum their elements' terms in the tiled kernel) against the oracle and the
+    element-kernel + scatter path, with a sampled source and without one, forward and adjoint."""
+    mesh = meshgen.permute_mesh(meshgen.structured_rectangle(96, 80, jitter=0.25, seed=9, topology=False))
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        basis = make_basis(mesh, order)
+    finally:
+        torch.set_default_dtype(previous)
+    coords, conn = mesh["vertices"], mesh["triangles"]
+    geo = fo.tri_geometry(coords, conn, order)
+    rng = np.random.default_rng(order)
+    grad = rng.standard_normal(geo["integration_points"].shape)
+    tol = 1e-12 if dtype == torch.float64 else 2e-5
+    for source, f_q in ((lambda x: torch.sin(3 * x[..., :1]) * torch.cos(2 * x[..., 1:2]),
+                         np.sin(3 * geo["integration_points"][..., :1]) * np.cos(2 * geo["integration_points"][..., 1:2])),
+                        (None, None)):
+        form = forms.WeakResidual(source) if source is not None else forms.WeakResidual(forms.Source())
+        ref = fo.scatter_linear(fo.quad_reduce(fo.form_weak_residual(geo, f_q if f_q is not None else 0.0 * geo["integration_points"][..., :1], grad),
+                                               geo["dx"]), conn, coords.shape[0])
+        results = {}
+        for path in ("tiled", "two_pass"):
+            basis.residual_path = path
+            gu = torch.tensor(grad, device=DEV, dtype=dtype, requires_grad=True)
+            r = basis.integrate_linear_form(form, gu)
+            assert relmax(r.detach().cpu().numpy(), ref) < tol, (path, order)
+            cot = rng.standard_normal(ref.shape)
+            (r * torch.tensor(cot, device=DEV, dtype=dtype)).sum().backward()
+            assert relmax(gu.grad.cpu().numpy(), fo.weak_residual_backward(geo, conn, cot)) < tol
+            results[path] = r.detach()
+        if dtype == torch.float64:  # both sum a row's terms in increasing element order
+            assert relmax(results["tiled"].cpu().numpy(), results["two_pass"].cpu().numpy()) < 1e-14
+
+
+def test_weak_residual_tiled_two_fractures():
+    """The same launch on a fracture network: grad u is 3-D, pulled back with J_f^+; rows glued along the trace."""
+    meshes, data = meshgen.two_fracture_network(32, 12)
+    v2 = np.stack([m["vertices"] for m in meshes])
+    conn = np.stack([m["triangles"] for m in meshes])
+    with api_checks.default_device(DEV):
+        mesh = tfem.FracturesTri(meshes, torch.tensor(data))
+        basis = tfem.FractureBasis(mesh, tfem.ElementTri(1, 4))
+    geo = fo.tri_geometry(v2, conn, 4, fracture=fo.fracture_map(v2, data))
+    tris = basis.global_triangulation["triangles"].cpu().numpy()
+    rng = np.random.default_rng(4)
+    grad = rng.standard_normal(geo["integration_points"].shape)
+    f_q = api_checks.rhs3_np(geo["integration_points"])
+    ref = fo.scatter_linear(fo.quad_reduce(fo.form_weak_residual(geo, f_q, grad), geo["dx"]), tris, basis.pattern.n_dof)
+    for path in ("tiled", "two_pass"):
+        basis.residual_path = path
+        r = basis.integrate_linear_form(forms.WeakResidual(api_checks.rhs3), torch.tensor(grad, device=DEV))
+        assert relmax(r.cpu().numpy().reshape(-1), ref.reshape(-1)) < 1e-12, path
 
 
 def test_patches_config3_size_fp32():

@@ -115,7 +115,9 @@ def main():
     with torch.device(DEV):
         mesh = tfem.FracturesTri(meshes, torch.tensor(data))
         basis = tfem.FractureBasis(mesh, tfem.ElementTri(1, 4))
-    residual_case(f"C4 two fractures {nx}x{ny} fp64", basis, 2 * 2 * nx * ny, 6, 3, 8, flush, rows)
+    for path in ("two_pass", "tiled"):  # element kernel + scatter | one launch of the tiled kernel (the default at this size)
+        basis.residual_path = path
+        residual_case(f"C4 two fractures {nx}x{ny} fp64 ({path})", basis, 2 * 2 * nx * ny, 6, 3, 8, flush, rows)
     del basis, mesh
 
     # ---- C5: seven fractures, stiffness + load (generic two-pass path) and the jump estimator ------------

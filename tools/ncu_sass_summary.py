@@ -22,6 +22,13 @@ def main(path, top=18):
     g["pct_inst"] = (100 * g.inst / total).round(1)
     g["pct_samples"] = (100 * g.samples / df["samples"].sum()).round(1)
     print(g.head(top).to_string())
+    # Blackwell / Hopper data-movement and synchronisation opcodes (static SASS lines | executed warp instructions)
+    full = src.str.split().str[0]
+    for label, pattern in (("UBLKCP (TMA bulk copy)", "UBLKCP"), ("LDGSTS (cp.async)", "LDGSTS"), ("SYNCS (mbarrier)", "SYNCS"),
+                           ("ATOMG / RED (global atomics)", "ATOMG|RED"), ("ATOMS (shared atomics)", "ATOMS"), ("BAR (block barrier)", "BAR"),
+                           ("LDS / STS", "LDS|STS"), ("LDG / STG", "LDG|STG"), ("MUFU", "MUFU"), ("VOTE / REDUX", "VOTE|REDUX|CREDUX")):
+        mask = full.str.contains("^(?:" + pattern + ")", regex=True, na=False)
+        print(f"  {label:34s} {int(mask.sum()):5d} lines  {df.loc[mask, 'inst'].sum():14.0f} executed")
     stall_cols = [c for c in df.columns if c.startswith("stall_") and "Not Issued" not in c]
     stalls = pd.Series({c: num(c).sum() for c in stall_cols}).sort_values(ascending=False)
     print((100 * stalls / stalls.sum()).round(1).head(8).to_string())
