@@ -413,7 +413,8 @@ class AbstractBasis(abc.ABC):
         counts = torch.bincount(new_row, minlength=inner.numel())
         new_crow = torch.zeros(inner.numel() + 1, dtype=crow.dtype, device=col.device)
         new_crow[1:] = torch.cumsum(counts, 0)
-        return torch.sparse_csr_tensor(new_crow, rank[col.long()[keep]].to(col.dtype), val[keep], size=(inner.numel(), inner.numel()))
+        return torch.sparse_csr_tensor(new_crow, rank[col.long()[keep]].to(col.dtype), val[keep], size=(inner.numel(), inner.numel()),
+                                       device=val.device)  # (explicit: a default-device context must not move the result)
 
     def reshape_for_assembly(self, local_matrices: torch.Tensor, form: str) -> torch.Tensor:
         """Flatten local matrices in COO order (reference :162-171)."""

@@ -316,7 +316,7 @@ class TilePlan:
     elem_order: int = 1  # 1 = tile elements in ascending id, 2 = even positions first, then odd
     layout_stats: dict = None  # modelled shared-memory wavefronts of the representative tile's reduction phase
     has_elem_ids: bool = False  # instances carry the global id of every tile element (sampled sources, fractures)
-    consumer_threads: int = 0  # compute threads per CTA (256 / 384 / 512); 0 = library default
+    consumer_threads: int = 0  # kernel selector: 0 = library default, 384 = classic kernel, 100 * NB + NC = role-specialised
     tile_of_row: torch.Tensor = None  # (n_dof,) tile owning each CSR row
     tile_list: torch.Tensor = None  # optional (n,) int32 subset / order of tiles to run (see `subset`)
     reserve_ctas: int = 0  # CTA slots left free for kernels on other streams while this plan runs
@@ -361,7 +361,8 @@ class TilePlan:
     @property
     def consumer_warps(self) -> int:
         """Warps that report per finished tile on `progress`."""
-        return (int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)) or default_consumers(self.max_elem)) // 32
+        consumers = int(os.environ.get("TFEM_TILED_CONSUMERS", self.consumer_threads)) or default_consumers(self.max_elem)
+        return consumers % 100 if consumers >= 1000 else consumers // 32  # role-specialised kernel: its reduction warps report
 
     def to(self, device) -> "TilePlan":
         moved = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in self.__dict__.items() if not k.startswith("_")}
@@ -438,8 +439,9 @@ def _layout_for_tile(t, ent_tile, ent_code, ent_cnt, c_ent, c_within, c_loc, slo
 
 
 def default_consumers(max_elem: int) -> int:
-    """Compute threads per CTA the library picks for a plan (mirrors assemble_tiled.cu)."""
-    return 384
+    """Kernel the library picks for a plan (mirrors assemble_tiled.cu): 100 * NB + NC = the role-specialised kernel with
+    NB integration and NC reduction warps; 384 = the classic kernel with that many consumer threads."""
+    return 1212
 
 
 class TileTooLarge(ValueError):

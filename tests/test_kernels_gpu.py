@@ -168,12 +168,8 @@ def test_weak_residual_tiled_one_launch(order, dtype):
     """`tfem_weak_residual_tiled` (rows sum their elements' terms in the tiled kernel) against the oracle and the
     element-kernel + scatter path, with a sampled source and without one, forward and adjoint."""
     mesh = meshgen.permute_mesh(meshgen.structured_rectangle(96, 80, jitter=0.25, seed=9, topology=False))
-    previous = torch.get_default_dtype()
-    torch.set_default_dtype(dtype)
-    try:
-        basis = make_basis(mesh, order)
-    finally:
-        torch.set_default_dtype(previous)
+    basis = make_basis(mesh, order, dtype)
+    assert basis.dtype == dtype
     coords, conn = mesh["vertices"], mesh["triangles"]
     geo = fo.tri_geometry(coords, conn, order)
     rng = np.random.default_rng(order)

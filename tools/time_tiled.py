@@ -114,7 +114,12 @@ def main():
                     prod = [table[i] / max(ctas.value, 1) for i in range(8)]  # the CTA counter grows by one per CTA per launch
                     cons = [table[8 + i] / max(ctas.value, 1) for i in range(8)]
                     print("    producer cycles/CTA/launch: wait done %.0f | wait inst %.0f | issue gather %.0f | template %.0f | base+arrive %.0f" % tuple(prod[:5]))
-                    print("    consumer thread 0 cycles/CTA/launch: wait full+header %.0f | B %.0f | wait TC/inst %.0f | C entries %.0f | C rows %.0f | barrier %.0f" % tuple(cons[:6]))
+                    if consumers >= 1000:  # role-specialised kernel: thread 0 of the integration group, thread 0 of the reduction group
+                        print("    integration thread 0: wait full %.0f | wait table free %.0f | B %.0f   reduction thread 0: wait B %.0f | C %.0f"
+                              % (cons[0], cons[1], cons[2], cons[4], cons[5]))
+                    else:
+                        print("    consumer thread 0 cycles/CTA/launch: wait full %.0f | header %.0f | B + barrier %.0f | wait TC %.0f | (unused) %.0f | C %.0f | end barrier %.0f"
+                              % tuple(cons[:7]))
 
 
 if __name__ == "__main__":
