@@ -127,13 +127,19 @@ typedef struct tfem_tile_plan {
                                (needed by tfem_tri_p1_assemble_csr_ex with a sampled source or fracture metrics) */
   int32_t table_bytes;      /* size of the CTA's local table in fp64 bytes (the fp32 kernels use half) */
   int32_t od_base[3];       /* byte offsets of the off-diagonal arrays K01, K12, K20 inside the table (see below) */
-  int32_t consumer_threads; /* 256, 384 or 512 compute threads per CTA; 0 = library default (384) */
+  int32_t consumer_threads; /* kernel selector: 0 = library default (the role-specialised kernel, 12 integration +
+                               12 reduction warps, one CTA per SM; plans too large for its shared memory run on the
+                               classic kernel); 384 = classic kernel, 384 compute threads, two CTAs per SM;
+                               100 * NB + NC = role-specialised kernel with NB + NC warps (1212 is built) */
   int32_t reserve_ctas;     /* CTA slots of the persistent grid left free so that kernels on other streams
-                               (interface pack / signal / add) can run beside it; 0 = use every slot */
+                               (interface pack / signal / add) can run beside it; 0 = use every slot.  Counted in
+                               slots of the classic kernel (two per SM): the role-specialised kernel leaves
+                               (reserve_ctas + 1) / 2 SMs free */
   int32_t n_progress_tiles; /* the first n_progress_tiles tiles of the call (in tile_list order) report on
-                               `progress` when they are finished: every consumer warp adds 1 after its stores
-                               (release), so the counter grows by n_progress_tiles * consumer_threads / 32 per
-                               call; 0 = nobody reports */
+                               `progress` when they are finished: every reduction warp adds 1 after its stores
+                               (release), so the counter grows by n_progress_tiles * 12 per call (12 = reduction
+                               warps of both built kernels; in general NC, or consumer_threads / 32 for the
+                               classic kernel); 0 = nobody reports */
   uint32_t* progress;       /* device counter, never reset by the library (callers wait for a growing target
                                with tfem_iface_pack_after); NULL = nobody reports */
 } tfem_tile_plan;

@@ -97,7 +97,36 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifndef TFEM_WAIT_SLEEP_NS
+#define TFEM_WAIT_SLEEP_NS 0
+#endif
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if TFEM_WAIT_SLEEP_NS > 0
+  // poll at a fixed interval instead of the hardware's wake-on-every-arrival (a barrier with N arrivals per phase wakes
+  // each waiting warp N times: issue slots the integration warps need)
+  if (mbar_test(bar, parity)) return;
+  uint64_t started_at = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    __nanosleep(TFEM_WAIT_SLEEP_NS);
+    if (mbar_test(bar, parity)) return;
+    if ((spin & 0x3fffu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (started_at == 0) started_at = now;
+      else if (now - started_at > 4000000000ull) __trap();
+    }
+  }
+#endif
   uint32_t done = 0;
   uint64_t started = 0;
   for (uint32_t spin = 1; !done; ++spin) {

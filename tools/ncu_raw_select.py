@@ -33,7 +33,7 @@ def main(src, dst, traffic=None):
         wr = get("dram__bytes_write.sum") * scale[units[header.index("dram__bytes_write.sum")]]
         json.dump({
             "kernel": values[header.index("Kernel Name")],
-            "source": f"profiles/{dst.split('/')[-1]} (ncu --set full --clock-control none, 1 launch, config 2, rows_per_tile=192)",
+            "source": f"profiles/{dst.split('/')[-1]} (ncu --set full --clock-control none, 1 launch, config 2, rows_per_tile=336)",
             "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": rd + wr,
             "gpu_time_us_under_ncu": get("gpu__time_duration.sum"),
             "registers_per_thread": get("launch__registers_per_thread"),
