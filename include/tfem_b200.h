@@ -326,6 +326,19 @@ TFEM_DECLARE(float, f32)
  * key[9e+3i+j] = dof_conn[e][j] * n_dof + dof_conn[e][i]   (row-major (row, col)). */
 int tfem_coo_keys(int64_t n_el, const int32_t* dof_conn, int64_t n_dof, int64_t* keys, void* stream);
 
+/* The whole symbolic phase of the sparse system on the device (SURVEY 8(b) tfem_csr_symbolic): the sorted-unique CSR
+ * pattern of bilinear_form_idx (basis/basis.py:72-77) and the stable COO -> CSR permutations the deterministic scatter
+ * kernels walk -- CUB radix sort of the (row, col) keys, run-length encoding, prefix sums, binary searches.
+ *   dof_conn [n_el,3] int32, DOFs 0 .. n_dof-1.  Outputs, sized for the worst case (the caller slices by *nnz):
+ *   crow [n_dof+1], col [9 n_el] (first nnz valid), seg [9 n_el + 1] (first nnz + 1 valid: COO entries perm[seg[p] ..
+ *   seg[p+1]) sum to CSR entry p, in increasing COO index), perm [9 n_el], lin_seg [n_dof+1] / lin_perm [3 n_el] (the same
+ *   for linear_form_idx), keys [9 n_el] (the nnz sorted unique keys row * n_dof + col), nnz (DEVICE int64).
+ * workspace: device scratch of at least tfem_csr_symbolic_workspace() bytes (the library never allocates). */
+int tfem_csr_symbolic_workspace(int64_t n_el, int64_t n_dof, int64_t* bytes);
+int tfem_csr_symbolic(int64_t n_el, const int32_t* dof_conn, int64_t n_dof, void* workspace, int64_t workspace_bytes,
+                      int32_t* crow, int32_t* col, int32_t* seg, int32_t* perm, int32_t* lin_seg, int32_t* lin_perm,
+                      int64_t* keys, int64_t* nnz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,8 @@ _TYPED = {
 }
 _UNTYPED = {
     "tfem_coo_keys": ([I64, P, I64, P, P], c_int),
+    "tfem_csr_symbolic_workspace": ([I64, I64, POINTER(c_int64)], c_int),
+    "tfem_csr_symbolic": ([I64, P, I64, P, I64, P, P, P, P, P, P, P, P, P], c_int),
     "tfem_abi_version": ([], c_int),
     "tfem_status_string": ([c_int], c_char_p),
     "tfem_set_device": ([c_int], c_int),

@@ -12,6 +12,7 @@ Structural zeros are kept: the pattern never depends on values.
 
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -81,6 +82,8 @@ def build_pattern(dof_conn: torch.Tensor, n_dof: int, extra_keys: torch.Tensor |
     if 9 * n_el >= 2**31:
         raise ValueError("mesh too large for 32-bit COO indices")
     device = conn.device
+    if conn.is_cuda and n_el > 0 and (extra_keys is None or not extra_keys.numel()) and os.environ.get("TFEM_SYMBOLIC", "native") == "native":
+        return _build_pattern_native(conn.to(torch.int32).contiguous(), n_dof)
     keys = _coo_keys(conn.to(torch.int32) if conn.is_cuda else conn, n_dof)
     sorted_keys, perm = torch.sort(keys, stable=True)
     uniq, counts = torch.unique_consecutive(sorted_keys, return_counts=True)
@@ -114,6 +117,31 @@ def build_pattern(dof_conn: torch.Tensor, n_dof: int, extra_keys: torch.Tensor |
         lin_perm=lin_perm.to(torch.int32),
         keys=uniq,
     )
+
+
+def _build_pattern_native(conn: torch.Tensor, n_dof: int) -> CsrPattern:
+    """`build_pattern` in one C-ABI call (`tfem_csr_symbolic`: CUB radix sort / run-length encode / scans on the
+    device); bit-identical to the torch program above (tests/test_kernels_gpu.py::test_native_symbolic_phase)."""
+    import ctypes
+
+    n_el = conn.shape[0]
+    device = conn.device
+    lib = _lib.load()
+    need = ctypes.c_int64()
+    if lib.tfem_csr_symbolic_workspace(n_el, n_dof, ctypes.byref(need)) != 0:
+        raise _lib.TfemError("tfem_csr_symbolic_workspace failed")
+    i32 = dict(dtype=torch.int32, device=device)
+    workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
+    crow, lin_seg = torch.empty(n_dof + 1, **i32), torch.empty(n_dof + 1, **i32)
+    col, seg, perm = torch.empty(9 * n_el, **i32), torch.empty(9 * n_el + 1, **i32), torch.empty(9 * n_el, **i32)
+    lin_perm = torch.empty(3 * n_el, **i32)
+    keys = torch.empty(9 * n_el, dtype=torch.int64, device=device)
+    nnz_dev = torch.zeros(1, dtype=torch.int64, device=device)
+    _lib.call("tfem_csr_symbolic", None, device, n_el, conn.data_ptr(), n_dof, workspace.data_ptr(), need.value, crow.data_ptr(), col.data_ptr(),
+              seg.data_ptr(), perm.data_ptr(), lin_seg.data_ptr(), lin_perm.data_ptr(), keys.data_ptr(), nnz_dev.data_ptr())
+    nnz = int(nnz_dev.item())  # the one synchronisation of the (one-time) symbolic phase
+    return CsrPattern(n_dof=n_dof, n_el=n_el, nnz=nnz, crow=crow, col=col[:nnz].clone(), seg=seg[: nnz + 1].clone(), perm=perm,
+                      lin_seg=lin_seg, lin_perm=lin_perm, keys=keys[:nnz].clone())
 
 
 def build_tile_plan(*args, **kwargs):

@@ -104,15 +104,41 @@ def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_a
         ra = np.concatenate([row_active, np.zeros((pad, 7), dtype=bool)]).reshape(-1, 32, 7)
         rows_wf = sum(_conflict_wavefronts(rr[:, :, j], rk[:, :, j], ra[:, :, j], 8, lambda k, r: (3 * r + k) % 8) for j in range(7))
         er = remap(entry_rows)
-        for s1 in range(16):
-            for s2 in range(16):
-                _, od_base, _ = table_layout(max_elem, (0, s1, s2))
-                base8 = np.array(od_base) // 8
-                wf = sum(_conflict_wavefronts(er[c], entry_slots[c] - 3, entry_active[c], 16, lambda k, r: (base8[k] + r) % 16) for c in range(2))
-                if best is None or wf + rows_wf < best[0]:
-                    best = (wf + rows_wf, order, (0, s1, s2), wf, rows_wf)
+        wf_all = _entry_wavefronts_all_shifts(er, entry_slots - 3, entry_active, max_elem)  # (16, 16): shifts of K12, K20
+        flat = int(np.argmin(wf_all))  # first minimum in (s1, s2) order, as a nested loop with a strict "<" would pick
+        s1, s2 = divmod(flat, 16)
+        wf = int(wf_all[s1, s2])
+        if best is None or wf + rows_wf < best[0]:
+            best = (wf + rows_wf, order, (0, s1, s2), wf, rows_wf)
         stats[order] = rows_wf
     return best[1], best[2], {"entries": best[3], "rows": best[4]}
+
+
+def _entry_wavefronts_all_shifts(rows, kinds, active, max_elem):
+    """Wavefronts of the entry phase's two table loads (`_conflict_wavefronts` with 16 lanes per group and bank
+    `(od_base[kind] / 8 + row) % 16`) for all 16 x 16 base shifts of the K12 / K20 arrays at once: which lanes share an
+    address does not depend on the shifts, only the banks do."""
+    import numpy as np
+
+    _, od_base, _ = table_layout(max_elem, (0, 0, 0))
+    base8 = np.array(od_base) // 8
+    shifts = np.arange(16)
+    total = np.zeros((16, 16), dtype=np.int64)
+    earlier = np.tril(np.ones((16, 16), dtype=bool), -1)
+    for c in range(rows.shape[0]):
+        row = rows[c].reshape(-1, 16)
+        kind = kinds[c].reshape(-1, 16)
+        act = active[c].reshape(-1, 16)
+        key = kind.astype(np.int64) * (1 << 20) + row
+        same = key[:, :, None] == key[:, None, :]
+        first = act & ~(same & earlier[None] & act[:, None, :]).any(axis=2)  # (G, 16): first lane of each distinct address
+        bank0 = base8[kind] + row  # (G, 16)
+        shift = np.where(kind == 1, shifts[:, None, None, None], 0) + np.where(kind == 2, shifts[None, :, None, None], 0)
+        bank = (bank0[None, None] + shift) % 16  # (16, 16, G, 16)
+        onehot = (bank[..., None] == shifts) & first[None, None, :, :, None]  # (16, 16, G, lanes, banks)
+        worst = onehot.sum(axis=3).max(axis=3)  # (16, 16, G)
+        total += np.maximum(worst, act.any(axis=1)[None, None]).sum(axis=2)
+    return total
 
 MAX_SEGS = 2047  # 16-bit entry codes seg * 32 + lane, 0xFFFF = none
 

@@ -523,6 +523,33 @@ def test_h1_error_functional_fused_matches_generic():
         assert relmax(fused.cpu().numpy(), ref) < 1e-12
 
 
+@pytest.mark.parametrize("kind", ["structured", "permuted", "delaunay", "fan"])
+def test_native_symbolic_phase(kind, monkeypatch):
+    """`tfem_csr_symbolic` (CUB sort / run-length encode / scans on the device) against the torch program it replaces:
+    every array of the pattern bit-identical."""
+    from pytorch_fem_solver_b200 import csr
+
+    if kind == "structured":
+        mesh = meshgen.structured_rectangle(97, 53, topology=False)
+    elif kind == "permuted":
+        mesh = meshgen.permute_mesh(meshgen.structured_rectangle(64, 40, jitter=0.2, topology=False))
+    elif kind == "delaunay":
+        mesh = meshgen.delaunay_unit_square(400, seed=3)
+    else:  # 23 triangles around one vertex: a row with 24 entries, a DOF with 23 linear-form terms
+        angles = np.linspace(0.0, 2.0 * np.pi, 24)[:-1]
+        ring = np.stack([np.cos(angles), np.sin(angles)], axis=1)
+        mesh = {"vertices": np.concatenate([[[0.0, 0.0]], ring]), "triangles": np.array([[0, 1 + i, 1 + (i + 1) % 23] for i in range(23)], dtype=np.int32)}
+    conn = torch.tensor(np.asarray(mesh["triangles"]), dtype=torch.int32, device=DEV)
+    n_dof = int(np.asarray(mesh["vertices"]).shape[0])
+    native = csr.build_pattern(conn, n_dof)
+    monkeypatch.setenv("TFEM_SYMBOLIC", "torch")
+    ref = csr.build_pattern(conn, n_dof)
+    assert native.nnz == ref.nnz
+    for name in ("crow", "col", "seg", "perm", "lin_seg", "lin_perm", "keys"):
+        a, b = getattr(native, name), getattr(ref, name)
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), name
+
+
 def test_reduce_keeps_csr_sparse():
     """`reduce` of a CSR operator returns the interior block in compact numbering without densifying."""
     mesh = meshgen.structured_rectangle(12, 9, jitter=0.2, seed=1)
