@@ -317,7 +317,24 @@ int tfem_sm_count(void);
    * scal[1] = r.z (scal[0] is overwritten); after a call scal[1] holds the new r.z. */           \
   int tfem_cg_iteration_##SUF(int64_t n, const int32_t* crow, const int32_t* col, const T* val,    \
                               const uint8_t* keep, const T* inv_diag, T* x, T* r, T* z, T* p,      \
-                              T* ap, T* partial, int32_t n_partial, T* scal, void* stream);
+                              T* ap, T* partial, int32_t n_partial, T* scal, void* stream);      \
+  /* SURVEY.md 8(f).3 -- fused MLP-at-quadrature-points producer: N(x) and dN/dx of the body of the\
+   * reference's FeedForwardNeuralNetwork (model/neural_network.py:50-100: Linear(d,w) act         \
+   * {Linear(w,w) act} x n_square Linear(w,1)) by forward-mode differentiation in one pass over    \
+   * the points: no autograd graph, no per-layer activation tensors.  params: W0 [w][d] | b0 [w] | \
+   * {Wk [w][w] | bk [w]} x n_square | w_out [w] | b_out [1] (torch.nn.Linear layout);             \
+   * act 0 = tanh, 1 = ReLU; d = 1..3, w <= 32.  x [n_pts,d] -> value [n_pts], grad [n_pts,d]. */  \
+  int tfem_mlp_value_grad_##SUF(int64_t n_pts, int d, int width, int n_square, int act,            \
+                                const T* params, const T* x, T* value, T* grad, void* stream);     \
+  /* Its adjoint with respect to the parameters (what loss.backward() needs; the double backward   \
+   * of neural_network.py:85-100 with create_graph=True): params_bar [n_params] from value_bar     \
+   * [n_pts] and grad_bar [n_pts,d].  partial: scratch of n_partial * n_params values (n_partial = \
+   * thread blocks used, e.g. one per SM); the blocks' sums are added in block order               \
+   * (reproducible).  n_square <= 7. */                                                            \
+  int tfem_mlp_value_grad_bwd_##SUF(int64_t n_pts, int d, int width, int n_square, int act,        \
+                                    const T* params, const T* x, const T* value_bar,               \
+                                    const T* grad_bar, T* partial, int n_partial, T* params_bar,   \
+                                    void* stream);
 
 TFEM_DECLARE(double, f64)
 TFEM_DECLARE(float, f32)

@@ -88,6 +88,8 @@ _TYPED = {
     "tfem_edge_jump": [I64, c_int, c_int, P, P, P, P, P, P],
     "tfem_csr_spmv": [I64, P, P, P, P, P, P, P],
     "tfem_cg_iteration": [I64, P, P, P, P, P, P, P, P, P, P, P, c_int32, P, P],
+    "tfem_mlp_value_grad": [I64, c_int, c_int, c_int, c_int, P, P, P, P, P],
+    "tfem_mlp_value_grad_bwd": [I64, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P],
     "tfem_iface_pack": [I64, P, P, P, P],
     "tfem_iface_pack_after": [I64, P, P, P, P, c_uint32, P],
     "tfem_iface_unpack_add": [I64, P, P, P, P],

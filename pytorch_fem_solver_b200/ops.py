@@ -588,6 +588,77 @@ def _(u, grad_u, u_ex, grad_ex, coords, conn, n_el_per_mesh, n_vert_per_mesh, qu
 
 
 # ------------------------------------------------------------------------------------------------
+# fused MLP producer
+# ------------------------------------------------------------------------------------------------
+ACT_TANH, ACT_RELU = 0, 1
+MLP_MAX_WIDTH, MLP_MAX_SQUARE_BWD = 32, 7
+
+
+def mlp_param_count(d: int, width: int, n_square: int) -> int:
+    return width * d + width + n_square * (width * width + width) + width + 1
+
+
+@torch.library.custom_op(f"{NS}::mlp_value_grad", mutates_args=())
+def mlp_value_grad(params: Tensor, x: Tensor, width: int, n_square: int, act: int) -> Tuple[Tensor, Tensor]:
+    """N(x) (M,) and dN/dx (M,d) of the MLP Linear(d,w) act {Linear(w,w) act} x n_square Linear(w,1) whose parameters
+    are packed in `params` (torch.nn.Linear layout, in network order), by forward-mode differentiation in ONE kernel
+    (`tfem_mlp_value_grad`).  Differentiable with respect to `params` (not `x`: the points are quadrature points)."""
+    device = check_cuda(params, x)
+    n_pts, d = x.shape
+    if params.numel() != mlp_param_count(d, width, n_square) or params.dtype != x.dtype:
+        raise TfemError(f"mlp_value_grad: expected {mlp_param_count(d, width, n_square)} packed parameters of dtype {x.dtype}")
+    value = torch.empty((n_pts,), dtype=x.dtype, device=device)
+    grad = torch.empty((n_pts, d), dtype=x.dtype, device=device)
+    call("tfem_mlp_value_grad", x.dtype, device, n_pts, d, width, n_square, act, ptr(params), ptr(x), ptr(value), ptr(grad))
+    return value, grad
+
+
+@mlp_value_grad.register_fake
+def _(params, x, width, n_square, act):
+    return x.new_empty((x.shape[0],)), x.new_empty(x.shape)
+
+
+@torch.library.custom_op(f"{NS}::mlp_value_grad_bwd", mutates_args=())
+def mlp_value_grad_bwd(params: Tensor, x: Tensor, value_bar: Tensor, grad_bar: Tensor, width: int, n_square: int, act: int) -> Tensor:
+    """Adjoint of `mlp_value_grad` with respect to the packed parameters (`tfem_mlp_value_grad_bwd`)."""
+    device = check_cuda(params, x, value_bar, grad_bar)
+    n_pts, d = x.shape
+    n_partial = _lib.load().tfem_sm_count()
+    if n_partial <= 0:
+        raise TfemError("tfem_sm_count failed")
+    partial = torch.empty((n_partial, params.numel()), dtype=x.dtype, device=device)
+    out = torch.empty_like(params)
+    call("tfem_mlp_value_grad_bwd", x.dtype, device, n_pts, d, width, n_square, act, ptr(params), ptr(x), ptr(value_bar), ptr(grad_bar),
+         ptr(partial), n_partial, ptr(out))
+    return out
+
+
+@mlp_value_grad_bwd.register_fake
+def _(params, x, value_bar, grad_bar, width, n_square, act):
+    return torch.empty_like(params)
+
+
+def _mlp_setup(ctx, inputs, output):
+    params, x, width, n_square, act = inputs
+    ctx.save_for_backward(params, x)
+    ctx.meta = (width, n_square, act)
+
+
+def _mlp_backward(ctx, value_bar, grad_bar):
+    params, x = ctx.saved_tensors
+    width, n_square, act = ctx.meta
+    if value_bar is None:
+        value_bar = torch.zeros(x.shape[0], dtype=x.dtype, device=x.device)
+    if grad_bar is None:
+        grad_bar = torch.zeros_like(x)
+    out = mlp_value_grad_bwd(params, x, value_bar.contiguous(), grad_bar.contiguous(), width, n_square, act)
+    return out, None, None, None, None
+
+
+mlp_value_grad.register_autograd(_mlp_backward, setup_context=_mlp_setup)
+
+
+# ------------------------------------------------------------------------------------------------
 # interpolation / jump
 # ------------------------------------------------------------------------------------------------
 

@@ -120,6 +120,42 @@ def main():
         residual_case(f"C4 two fractures {nx}x{ny} fp64 ({path})", basis, 2 * 2 * nx * ny, 6, 3, 8, flush, rows)
     del basis, mesh
 
+    # ---- C4 producer: u_NN and grad u_NN at the 6.3 M quadrature points, MLP 3 -> 25 x 7 -> 1 ReLU x BC, and the parameter
+    # gradients of a loss of both (example_fracture_vpinns.py:30-46,259): fused forward-mode kernel + hand-written adjoint
+    # against the reference's autograd route (torch double backward)
+    class Bc3(torch.nn.Module):
+        def forward(self, x):
+            return (x[..., :1] ** 2 - 1.0) * x[..., 1:2] * (x[..., 1:2] - 1.0) * (x[..., 2:3] ** 2 - 1.0)
+
+    torch.manual_seed(0)
+    net = tfem.FeedForwardNeuralNetwork(3, 1, 6, 25, activation_function=torch.nn.ReLU(), boundary_condition_modifier=Bc3()).to(device=DEV, dtype=torch.float64)
+    meshes, data = meshgen.two_fracture_network(nx, ny)
+    with torch.device(DEV):
+        mesh = tfem.FracturesTri(meshes, torch.tensor(data))
+        basis = tfem.FractureBasis(mesh, tfem.ElementTri(1, 4))
+    points = basis.integration_points
+    n_pts = points.numel() // 3
+
+    def mlp_forward():
+        with torch.no_grad():
+            return net.value_and_gradient(points)
+
+    def mlp_step():
+        value, gradient = net.value_and_gradient(points)
+        loss = (value**2).sum() + (gradient**2).sum()
+        return torch.autograd.grad(loss, list(net.parameters()))
+
+    for path in ("auto", "torch"):
+        net.gradient_path = path
+        label = "fused kernels" if path == "auto" else "torch autograd (reference route)"
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        t_f = timed(mlp_forward, 3, None)
+        t_s = timed(mlp_step, 3, None)
+        rows.append({"case": f"C4 MLP 3->25x7->1 ReLU at {n_pts} points, {label}", "elements": n_pts, "us_value_and_gradient": round(t_f, 1),
+                     "us_with_parameter_gradients": round(t_s, 1), "peak_extra_GB": round((torch.cuda.max_memory_allocated() - base) / 1e9, 2)})
+    del basis, mesh, net, points
+
     # ---- C5: seven fractures, stiffness + load (generic two-pass path) and the jump estimator ------------
     nx, ny = max(int(1024 * args.scale) // 8 * 8, 8), max(int(586 * args.scale), 2)
     meshes, data = meshgen.seven_fracture_network(nx, ny)
