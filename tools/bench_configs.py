@@ -137,8 +137,7 @@ def main():
     n_pts = points.numel() // 3
 
     def mlp_forward():
-        with torch.no_grad():
-            return net.value_and_gradient(points)
+        return net.value_and_gradient(points)
 
     def mlp_step():
         value, gradient = net.value_and_gradient(points)
