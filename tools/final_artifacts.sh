@@ -9,4 +9,5 @@ python tools/bench_configs.py > gpurun_out/final_aux_configs.jsonl 2>/dev/null; 
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/plain_final.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list_final.log 2>&1
 grep -c assemble_tiled gpurun_out/final_launches.csv
-bash tools/profile_tiled.sh final --libs default | tail -2
+bash tools/profile_tiled.sh final --libs default --consumers 0 | tail -2
+python tools/time_symbolic.py 2>/dev/null | tee gpurun_out/final_symbolic.txt
