@@ -356,6 +356,32 @@ int tfem_csr_symbolic(int64_t n_el, const int32_t* dof_conn, int64_t n_dof, void
                       int32_t* crow, int32_t* col, int32_t* seg, int32_t* perm, int32_t* lin_seg, int32_t* lin_perm,
                       int64_t* keys, int64_t* nnz, void* stream);
 
+/* SURVEY 8(f).2 -- edge topology on the device, replacing AbstractMesh._compute_interior_and_boundary_edges /
+ * _compute_cells_4_edges (mesh/abstract_mesh.py:104-255, mesh/meshes_tri.py:54-123).
+ * tfem_half_edges: every cell edge of n_mesh stacked meshes (conn [n_mesh * n_cells, 3], mesh-local vertex ids;
+ *   local_pairs: HOST array of the 3 local vertex pairs, e.g. {0,1, 1,2, 0,2}) as the key
+ *   mesh * n_vert^2 + min(v) * n_vert + max(v), stably sorted with its cell (index within the mesh) as payload:
+ *   he_sorted / cell_sorted [3 n_mesh n_cells]; unique_keys / counts (same capacity, the first *n_unique valid;
+ *   counts = incidence, 1 = boundary edge); n_unique: DEVICE int64.  workspace >= tfem_half_edges_workspace() bytes.
+ * tfem_edge_cells: the n_sides (1 or 2) cells adjacent to each edge of edge_vertices [n_mesh * n_edges, 2], in increasing
+ *   cell id; *status (DEVICE int32, zeroed by the caller) collects 1 = an edge belongs to no cell, 2 = a two-sided edge
+ *   has a single adjacent cell.
+ * tfem_interior_edge_geometry: end points x [.,2,2], length [.], unit normal [.,2] of each interior edge, the normal
+ *   pointing from the first listed cell's centroid towards the second's (abstract_mesh.py:143-162). */
+int tfem_half_edges_workspace(int64_t n_mesh, int64_t n_cells, int64_t* bytes);
+int tfem_half_edges(int64_t n_mesh, int64_t n_cells, int64_t n_vert, const int32_t* conn, const int32_t* local_pairs,
+                    void* workspace, int64_t workspace_bytes, int64_t* he_sorted, int32_t* cell_sorted, int64_t* unique_keys,
+                    int32_t* counts, int64_t* n_unique, void* stream);
+int tfem_edge_cells(int64_t n_mesh, int64_t n_edges, int64_t n_vert, const int32_t* edge_vertices, int n_sides,
+                    const int64_t* he_sorted, const int32_t* cell_sorted, int64_t n_half, int32_t* cells, int32_t* status,
+                    void* stream);
+int tfem_interior_edge_geometry_f64(int64_t n_mesh, int64_t n_edges, int64_t n_vert, int64_t n_cells, const double* coords,
+                                    const int32_t* conn, const int32_t* edge_vertices, const int32_t* edge_cells, double* x,
+                                    double* length, double* normal, void* stream);
+int tfem_interior_edge_geometry_f32(int64_t n_mesh, int64_t n_edges, int64_t n_vert, int64_t n_cells, const float* coords,
+                                    const int32_t* conn, const int32_t* edge_vertices, const int32_t* edge_cells, float* x,
+                                    float* length, float* normal, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

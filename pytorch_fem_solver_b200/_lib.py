@@ -98,6 +98,11 @@ _UNTYPED = {
     "tfem_coo_keys": ([I64, P, I64, P, P], c_int),
     "tfem_csr_symbolic_workspace": ([I64, I64, POINTER(c_int64)], c_int),
     "tfem_csr_symbolic": ([I64, P, I64, P, I64, P, P, P, P, P, P, P, P, P], c_int),
+    "tfem_half_edges_workspace": ([I64, I64, POINTER(c_int64)], c_int),
+    "tfem_half_edges": ([I64, I64, I64, P, POINTER(c_int32), P, I64, P, P, P, P, P, P], c_int),
+    "tfem_edge_cells": ([I64, I64, I64, P, c_int, P, P, I64, P, P, P], c_int),
+    "tfem_interior_edge_geometry_f64": ([I64, I64, I64, I64, P, P, P, P, P, P, P, P], c_int),
+    "tfem_interior_edge_geometry_f32": ([I64, I64, I64, I64, P, P, P, P, P, P, P, P], c_int),
     "tfem_abi_version": ([], c_int),
     "tfem_status_string": ([c_int], c_char_p),
     "tfem_set_device": ([c_int], c_int),

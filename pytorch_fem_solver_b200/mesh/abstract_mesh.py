@@ -16,6 +16,7 @@ Mirrors the key layout and shapes of the reference's `AbstractMesh`
 from __future__ import annotations
 
 import abc
+import os
 from typing import Any
 
 import numpy as np
@@ -141,17 +142,28 @@ class AbstractMesh(abc.ABC):
         device = conn.device
         perms = self._edges_permutations.to(device)
 
-        # half-edge table, stably sorted by (mesh, min vertex, max vertex)
+        # half-edge table, stably sorted by (mesh, min vertex, max vertex): hand-written kernels + CUB on a CUDA device
+        # (`tfem_half_edges`, `tfem_edge_cells`, `tfem_interior_edge_geometry`), torch ops elsewhere
+        native = (device.type == "cuda" and coords.dtype in (torch.float64, torch.float32) and coords.shape[-1] == 2
+                  and 3 * n_mesh * n_cells < 2**31 and os.environ.get("TFEM_TOPOLOGY", "native") == "native")
         he = conn[:, :, perms]  # (F,N,3,2)
-        lo, hi = he.min(-1).values, he.max(-1).values
-        mesh_off = torch.arange(n_mesh, device=device).reshape(-1, 1, 1) * (n_vert * n_vert)
-        he_key = (mesh_off + lo * n_vert + hi).reshape(-1)
-        he_cell = torch.arange(n_cells, device=device).repeat_interleave(3).repeat(n_mesh)
-        he_sorted, he_order = torch.sort(he_key, stable=True)
-        cell_sorted = he_cell[he_order]
+        if native:
+            from .. import ops
+
+            conn32 = conn.to(torch.int32).contiguous()
+            he_sorted, cell_sorted, uniq, counts = ops.half_edges(conn32, n_vert, perms.tolist())
+        else:
+            lo, hi = he.min(-1).values, he.max(-1).values
+            mesh_off = torch.arange(n_mesh, device=device).reshape(-1, 1, 1) * (n_vert * n_vert)
+            he_key = (mesh_off + lo * n_vert + hi).reshape(-1)
+            he_cell = torch.arange(n_cells, device=device).repeat_interleave(3).repeat(n_mesh)
+            he_sorted, he_order = torch.sort(he_key, stable=True)
+            cell_sorted = he_cell[he_order]
+            uniq = counts = None
 
         if "vertices" not in td["edges"]:
-            uniq, counts = torch.unique_consecutive(he_sorted, return_counts=True)
+            if uniq is None:
+                uniq, counts = torch.unique_consecutive(he_sorted, return_counts=True)
             per_mesh = torch.bincount(torch.div(uniq, n_vert * n_vert, rounding_mode="floor"), minlength=n_mesh)
             if not bool((per_mesh == per_mesh[0]).all()):
                 raise ValueError("stacked meshes must have the same number of edges")
@@ -171,6 +183,8 @@ class AbstractMesh(abc.ABC):
         v_interior = edge_vertices[~boundary_mask].reshape(n_mesh, -1, 2)
 
         def cells_of(edge_list, n_sides):
+            if native:
+                return ops.edge_cells(edge_list.to(torch.int32).contiguous(), n_vert, n_sides, he_sorted, cell_sorted).long()
             e = edge_list.long()
             key = (
                 torch.arange(n_mesh, device=device).reshape(-1, 1) * (n_vert * n_vert)
@@ -191,17 +205,21 @@ class AbstractMesh(abc.ABC):
         c_boundary = cells_of(v_boundary, 1)
 
         batch = torch.arange(n_mesh, device=device).reshape(-1, 1, 1)
-        x_interior = coords[batch, v_interior.long()]  # (F,E_i,2,2)
         x_boundary = coords[batch, v_boundary.long()]
-        vec = x_interior[..., 1:2, :] - x_interior[..., 0:1, :]  # (F,E_i,1,2)
-        length = torch.linalg.vector_norm(vec, dim=-1, keepdim=True)
-        normal = torch.stack([-vec[..., 1], vec[..., 0]], dim=-1) / length
-        # orient from the first listed cell's centroid towards the second's (reference :143-162)
-        cell_x = self._flat(("cells", "coordinates"))
-        centroid = cell_x[batch, c_interior].mean(dim=-2)  # (F,E_i,2,2)
-        towards = centroid[..., 1:2, :] - centroid[..., 0:1, :]
-        flip = (normal * towards).sum(-1, keepdim=True) < 0
-        normal = torch.where(flip, -normal, normal)
+        if native:
+            x_interior, length, normal = ops.interior_edge_geometry(coords.contiguous(), conn32, v_interior.to(torch.int32).contiguous(),
+                                                                    c_interior.to(torch.int32).contiguous())
+        else:
+            x_interior = coords[batch, v_interior.long()]  # (F,E_i,2,2)
+            vec = x_interior[..., 1:2, :] - x_interior[..., 0:1, :]  # (F,E_i,1,2)
+            length = torch.linalg.vector_norm(vec, dim=-1, keepdim=True)
+            normal = torch.stack([-vec[..., 1], vec[..., 0]], dim=-1) / length
+            # orient from the first listed cell's centroid towards the second's (reference :143-162)
+            cell_x = self._flat(("cells", "coordinates"))
+            centroid = cell_x[batch, c_interior].mean(dim=-2)  # (F,E_i,2,2)
+            towards = centroid[..., 1:2, :] - centroid[..., 0:1, :]
+            flip = (normal * towards).sum(-1, keepdim=True) < 0
+            normal = torch.where(flip, -normal, normal)
 
         self._store(("interior_edges", "cells"), c_interior)
         self._store(("interior_edges", "vertices"), v_interior)

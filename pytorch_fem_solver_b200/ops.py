@@ -588,6 +588,64 @@ def _(u, grad_u, u_ex, grad_ex, coords, conn, n_el_per_mesh, n_vert_per_mesh, qu
 
 
 # ------------------------------------------------------------------------------------------------
+# edge topology: integer, one-time; plain functions (nothing to differentiate)
+# ------------------------------------------------------------------------------------------------
+def half_edges(conn: Tensor, n_vert: int, local_pairs) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """conn (F,N,3) int32 -> (he_sorted (3FN,) int64, cell_sorted (3FN,) int32, unique keys (E,) int64, incidence counts
+    (E,) int32) of the cell edges keyed `mesh * n_vert^2 + min * n_vert + max` (`tfem_half_edges`)."""
+    import ctypes
+
+    device = check_cuda(conn)
+    n_mesh, n_cells, _ = conn.shape
+    n_half = 3 * n_mesh * n_cells
+    lib = _lib.load()
+    need = ctypes.c_int64()
+    if lib.tfem_half_edges_workspace(n_mesh, n_cells, ctypes.byref(need)) != 0:
+        raise TfemError("tfem_half_edges_workspace failed")
+    workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
+    he_sorted = torch.empty(n_half, dtype=torch.int64, device=device)
+    cell_sorted = torch.empty(n_half, dtype=torch.int32, device=device)
+    uniq = torch.empty(n_half, dtype=torch.int64, device=device)
+    counts = torch.empty(n_half, dtype=torch.int32, device=device)
+    n_unique = torch.zeros(1, dtype=torch.int64, device=device)
+    pairs = (ctypes.c_int32 * 6)(*[int(v) for pair in local_pairs for v in pair])
+    call("tfem_half_edges", None, device, n_mesh, n_cells, n_vert, ptr(conn), pairs, ptr(workspace), need.value, ptr(he_sorted),
+         ptr(cell_sorted), ptr(uniq), ptr(counts), ptr(n_unique))
+    n = int(n_unique.item())
+    return he_sorted, cell_sorted, uniq[:n], counts[:n]
+
+
+def edge_cells(edge_vertices: Tensor, n_vert: int, n_sides: int, he_sorted: Tensor, cell_sorted: Tensor) -> Tensor:
+    """edge_vertices (F,E,2) int32 -> adjacent cells (F,E,n_sides) int32, sides in increasing cell id (`tfem_edge_cells`)."""
+    device = check_cuda(edge_vertices, he_sorted, cell_sorted)
+    n_mesh, n_edges, _ = edge_vertices.shape
+    cells = torch.empty((n_mesh, n_edges, n_sides), dtype=torch.int32, device=device)
+    status = torch.zeros(1, dtype=torch.int32, device=device)
+    call("tfem_edge_cells", None, device, n_mesh, n_edges, n_vert, ptr(edge_vertices), n_sides, ptr(he_sorted), ptr(cell_sorted),
+         he_sorted.numel(), ptr(cells), ptr(status))
+    flags = int(status.item())
+    if flags & 1:
+        raise ValueError("an edge of the edge list belongs to no cell")
+    if flags & 2:
+        raise ValueError("an edge marked interior has a single adjacent cell")
+    return cells
+
+
+def interior_edge_geometry(coords: Tensor, conn: Tensor, edge_vertices: Tensor, cells: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """coords (F,V,2), conn (F,N,3) int32, interior edges (F,E,2) int32 and their cells (F,E,2) int32 -> end points
+    (F,E,2,2), length (F,E,1,1), oriented unit normal (F,E,1,2) (`tfem_interior_edge_geometry`)."""
+    device = check_cuda(coords, conn, edge_vertices, cells)
+    n_mesh, n_edges, _ = edge_vertices.shape
+    opts = dict(dtype=coords.dtype, device=device)
+    x = torch.empty((n_mesh, n_edges, 2, 2), **opts)
+    length = torch.empty((n_mesh, n_edges, 1, 1), **opts)
+    normal = torch.empty((n_mesh, n_edges, 1, 2), **opts)
+    call("tfem_interior_edge_geometry", coords.dtype, device, n_mesh, n_edges, coords.shape[1], conn.shape[1], ptr(coords), ptr(conn),
+         ptr(edge_vertices), ptr(cells), ptr(x), ptr(length), ptr(normal))
+    return x, length, normal
+
+
+# ------------------------------------------------------------------------------------------------
 # fused MLP producer (SURVEY 8(f).3)
 # ------------------------------------------------------------------------------------------------
 ACT_TANH, ACT_RELU = 0, 1

@@ -550,6 +550,39 @@ def test_native_symbolic_phase(kind, monkeypatch):
         assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b), name
 
 
+@pytest.mark.parametrize("kind", ["structured", "listed_edges", "delaunay", "patches", "fractures"])
+def test_native_edge_topology(kind, monkeypatch):
+    """`tfem_half_edges` / `tfem_edge_cells` / `tfem_interior_edge_geometry` against the torch program they replace:
+    integer outputs bit-identical, lengths and normals to rounding."""
+
+    def build():
+        with api_checks.default_device(DEV):
+            if kind == "structured":
+                return tfem.MeshTri(meshgen.structured_rectangle(37, 23, jitter=0.2, seed=2, topology=False))
+            if kind == "listed_edges":
+                return tfem.MeshTri(meshgen.structured_rectangle(16, 9, jitter=0.2, seed=3))
+            if kind == "delaunay":
+                return tfem.MeshTri(meshgen.delaunay_unit_square(300, seed=5))
+            if kind == "patches":
+                centers, radius = meshgen.generate_patches_info(3)
+                return tfem.Patches(torch.tensor(centers), torch.tensor(radius))
+            meshes, data = meshgen.two_fracture_network(12, 5)
+            return tfem.FracturesTri(meshes, torch.tensor(data))
+
+    native = build()
+    monkeypatch.setenv("TFEM_TOPOLOGY", "torch")
+    ref = build()
+    for group, names in (("edges", ("vertices", "markers")), ("interior_edges", ("cells", "vertices", "coordinates", "length", "normals")),
+                         ("boundary_edges", ("cells", "vertices", "coordinates")), ("cells", ("length",))):
+        for name in names:
+            a, b = native[group, name], ref[group, name]
+            assert a.shape == b.shape and a.dtype == b.dtype and a.device == b.device, (group, name)
+            if a.dtype.is_floating_point:
+                assert float((a - b).abs().max()) <= 4e-16 * max(float(b.abs().max()), 1.0), (group, name)
+            else:
+                assert torch.equal(a, b), (group, name)
+
+
 def test_reduce_keeps_csr_sparse():
     """`reduce` of a CSR operator returns the interior block in compact numbering without densifying."""
     mesh = meshgen.structured_rectangle(12, 9, jitter=0.2, seed=1)
