@@ -1403,7 +1403,10 @@ int weak_residual_tiled(const tfem_tile_plan* hp, const T* coords, int quad_orde
   args.csr_val = nullptr;
   args.load = r;
   auto s = static_cast<cudaStream_t>(stream);
-  return dispatch_tiled_order<T>(hp->consumer_threads, quad_order, hp, args, cst, quad, s);
+  // the residual's integration phase streams grad u from global memory (latency-bound, not fp64-bound): the classic
+  // kernel's 24 integrating warps per SM keep more loads in flight than the 12 of the role-specialised one (C4 forward:
+  // 89 us against 145 us)
+  return dispatch_tiled_order<T>(hp->consumer_threads ? hp->consumer_threads : 384, quad_order, hp, args, cst, quad, s);
 }
 }  // namespace tfem
 
