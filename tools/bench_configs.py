@@ -44,10 +44,17 @@ def rhs3(points):
     return 6.0 * (y - y**2) * torch.abs(x) - 2.0 * (torch.abs(z) ** 3 - torch.abs(x)) + 1.0
 
 
-def residual_case(name, basis, n_el, n_q, d, size, flush, rows):
+def rhs2(points):
+    x, y = torch.split(points, 1, dim=-1)
+    return 2.0 * torch.pi**2 * torch.sin(torch.pi * x) * torch.sin(torch.pi * y)
+
+
+def residual_case(name, basis, n_el, n_q, d, size, flush, rows, analytic=False):
     """Weak residual r = sum_q dx (f v - grad v . grad u) to the DOF vector, and its adjoint."""
     grad_u = torch.randn(*basis.integration_points.shape[:-1], d, device=DEV, dtype=basis.dtype, requires_grad=True)
-    form = forms.WeakResidual() if d == 2 else forms.WeakResidual(rhs3)
+    # f as a callable, evaluated once at the basis' points and cached on the form (the reference evaluates rhs(x, y) in torch
+    # at every step, example_patches.py:102-113); `analytic=True` instead evaluates 2 pi^2 sin(pi x) sin(pi y) inside the kernel
+    form = (forms.WeakResidual() if analytic else forms.WeakResidual(rhs2)) if d == 2 else forms.WeakResidual(rhs3)
     r = basis.integrate_linear_form(form, grad_u)
     cot = torch.randn_like(r)
 
@@ -106,6 +113,8 @@ def main():
             patches = tfem.Patches(torch.tensor(centers, dtype=torch.float32), torch.tensor(radius, dtype=torch.float32))
             basis = tfem.PatchesBasis(patches, tfem.ElementTri(1, 4))
         residual_case(label, basis, 4 * len(centers), 6, 2, 4, flush if levels == 10 else None, rows)
+        if levels == 10:
+            residual_case(label + " (source evaluated in-kernel)", basis, 4 * len(centers), 6, 2, 4, flush, rows, analytic=True)
         del basis, patches
 
     # ---- C4: two fractures, 6-point quadrature, fp64 ----------------------------------------------------
