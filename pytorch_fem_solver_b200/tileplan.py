@@ -81,7 +81,7 @@ def _conflict_wavefronts(row, kind, active, lanes_per_group, group_bank):
     return int(np.maximum(counts.max(axis=1), act.any(axis=1)).sum())
 
 
-def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_active, n_elem, max_elem):
+def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_active, n_elem, max_elem, device=None):
     """Pick the element order inside a tile and the base shifts of the off-diagonal arrays that minimise the
     shared-memory wavefronts of the reduction phase on a representative tile.
 
@@ -104,7 +104,7 @@ def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_a
         ra = np.concatenate([row_active, np.zeros((pad, 7), dtype=bool)]).reshape(-1, 32, 7)
         rows_wf = sum(_conflict_wavefronts(rr[:, :, j], rk[:, :, j], ra[:, :, j], 8, lambda k, r: (3 * r + k) % 8) for j in range(7))
         er = remap(entry_rows)
-        wf_all = _entry_wavefronts_all_shifts(er, entry_slots - 3, entry_active, max_elem)  # (16, 16): shifts of K12, K20
+        wf_all = _entry_wavefronts_all_shifts(er, entry_slots - 3, entry_active, max_elem, device)  # (16, 16): shifts of K12, K20
         flat = int(np.argmin(wf_all))  # first minimum in (s1, s2) order, as a nested loop with a strict "<" would pick
         s1, s2 = divmod(flat, 16)
         wf = int(wf_all[s1, s2])
@@ -114,31 +114,34 @@ def _choose_layout(entry_rows, entry_slots, entry_active, row_rows, row_k, row_a
     return best[1], best[2], {"entries": best[3], "rows": best[4]}
 
 
-def _entry_wavefronts_all_shifts(rows, kinds, active, max_elem):
+def _entry_wavefronts_all_shifts(rows, kinds, active, max_elem, device=None):
     """Wavefronts of the entry phase's two table loads (`_conflict_wavefronts` with 16 lanes per group and bank
     `(od_base[kind] / 8 + row) % 16`) for all 16 x 16 base shifts of the K12 / K20 arrays at once: which lanes share an
-    address does not depend on the shifts, only the banks do."""
+    address does not depend on the shifts, only the banks do.  Evaluated with torch on `device` (the 10 M-element
+    one-hot costs 60 ms in numpy on the host, 1 ms on the GPU the plan is being built for)."""
     import numpy as np
 
     _, od_base, _ = table_layout(max_elem, (0, 0, 0))
-    base8 = np.array(od_base) // 8
-    shifts = np.arange(16)
-    total = np.zeros((16, 16), dtype=np.int64)
-    earlier = np.tril(np.ones((16, 16), dtype=bool), -1)
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    base8 = torch.tensor([b // 8 for b in od_base], dtype=torch.int64, device=dev)
+    shifts = torch.arange(16, device=dev)
+    total = torch.zeros((16, 16), dtype=torch.int64, device=dev)
+    earlier = torch.tril(torch.ones((16, 16), dtype=torch.bool, device=dev), -1)
     for c in range(rows.shape[0]):
-        row = rows[c].reshape(-1, 16)
-        kind = kinds[c].reshape(-1, 16)
-        act = active[c].reshape(-1, 16)
-        key = kind.astype(np.int64) * (1 << 20) + row
+        row = torch.as_tensor(np.ascontiguousarray(rows[c])).to(dev).reshape(-1, 16)
+        kind = torch.as_tensor(np.ascontiguousarray(kinds[c])).to(dev).reshape(-1, 16)
+        act = torch.as_tensor(np.ascontiguousarray(active[c])).to(dev).reshape(-1, 16)
+        key = kind * (1 << 20) + row
         same = key[:, :, None] == key[:, None, :]
-        first = act & ~(same & earlier[None] & act[:, None, :]).any(axis=2)  # (G, 16): first lane of each distinct address
+        first = act & ~(same & earlier[None] & act[:, None, :]).any(dim=2)  # (G, 16): first lane of each distinct address
         bank0 = base8[kind] + row  # (G, 16)
-        shift = np.where(kind == 1, shifts[:, None, None, None], 0) + np.where(kind == 2, shifts[None, :, None, None], 0)
+        shift = torch.where(kind == 1, shifts[:, None, None, None], 0) + torch.where(kind == 2, shifts[None, :, None, None], 0)
         bank = (bank0[None, None] + shift) % 16  # (16, 16, G, 16)
         onehot = (bank[..., None] == shifts) & first[None, None, :, :, None]  # (16, 16, G, lanes, banks)
-        worst = onehot.sum(axis=3).max(axis=3)  # (16, 16, G)
-        total += np.maximum(worst, act.any(axis=1)[None, None]).sum(axis=2)
-    return total
+        worst = onehot.sum(dim=3).amax(dim=3)  # (16, 16, G)
+        total += torch.maximum(worst, act.any(dim=1)[None, None].to(worst.dtype)).sum(dim=2)
+    return total.cpu().numpy()
+
 
 MAX_SEGS = 2047  # 16-bit entry codes seg * 32 + lane, 0xFFFF = none
 
@@ -461,7 +464,7 @@ def _layout_for_tile(t, ent_tile, ent_code, ent_cnt, c_ent, c_within, c_loc, slo
     row_k[local, within] = lc_k[sel].cpu().numpy()
     row_active = np.ones((n_rows, PER_CHUNK), dtype=bool)
     return _choose_layout(entry_rows.reshape(2, n_segs, SEG), entry_slots.reshape(2, n_segs, SEG), entry_active.reshape(2, n_segs, SEG),
-                          row_rows, row_k, row_active, n_elem, max_elem)
+                          row_rows, row_k, row_active, n_elem, max_elem, device=ent_tile.device)
 
 
 def default_consumers(max_elem: int) -> int:

@@ -34,3 +34,13 @@ os.environ["TFEM_SYMBOLIC"] = "native"
 same = all(torch.equal(getattr(pat, n), getattr(ref, n)) for n in ("crow", "col", "seg", "perm", "lin_seg", "lin_perm", "keys"))
 print("bit-identical:", same, "nnz", pat.nnz)
 timed("tile plan (336 rows per tile)", lambda: csr.build_tile_plan(conn, conn, pat, coords, 336, "auto"))
+if "--profile" in sys.argv:
+    import cProfile
+    import pstats
+
+    pr = cProfile.Profile()
+    pr.enable()
+    csr.build_tile_plan(conn, conn, pat, coords, 336, "auto")
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("tottime").print_stats(14)
