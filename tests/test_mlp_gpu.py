@@ -61,6 +61,34 @@ def test_fused_value_gradient_and_parameter_gradients(d, hidden, width, activati
         assert float((got.double() - want).abs().max()) <= tol * max(scale(want), scale(ref_grads[0])), (got.shape,)
 
 
+@pytest.mark.parametrize("name,activation", [("tanh2", torch.nn.Tanh()), ("relu3", torch.nn.ReLU())])
+def test_fused_kernels_against_the_reference_golden_vectors(name, activation):
+    """The kernels against outputs of the UNMODIFIED reference network (tests/golden/mlp_reference.npz)."""
+    import os
+
+    import numpy as np
+
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mlp_reference.npz"))
+    n = int(golden[f"{name}_n_layers"])
+    d, width = golden[f"{name}_w0"].shape[1], golden[f"{name}_w0"].shape[0]
+    net = tfem.FeedForwardNeuralNetwork(d, 1, n - 2, width, activation_function=activation).to(device=DEV, dtype=torch.float64)
+    linears = [m for m in net._neural_network if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for k, m in enumerate(linears):
+            m.weight.copy_(torch.from_numpy(golden[f"{name}_w{k}"]))
+            m.bias.copy_(torch.from_numpy(golden[f"{name}_b{k}"]))
+    points = torch.from_numpy(golden[f"{name}_points"]).to(DEV)
+    assert net._fused_spec(points) is not None
+    value, gradient = net.value_and_gradient(points)
+    assert float((value.cpu() - torch.from_numpy(golden[f"{name}_value"])).abs().max()) <= 1e-12 * float(np.abs(golden[f"{name}_value"]).max())
+    assert float((gradient.cpu() - torch.from_numpy(golden[f"{name}_gradient"])).abs().max()) <= 1e-12 * float(np.abs(golden[f"{name}_gradient"]).max())
+    loss = (value * torch.from_numpy(golden[f"{name}_cot_v"]).to(DEV)).sum() + (gradient * torch.from_numpy(golden[f"{name}_cot_g"]).to(DEV)).sum()
+    grads = torch.autograd.grad(loss, list(net.parameters()))
+    scale = max(float(np.abs(golden[f"{name}_grad{k}"]).max()) for k in range(2 * n))
+    for k, g in enumerate(grads):
+        assert float((g.cpu() - torch.from_numpy(golden[f"{name}_grad{k}"])).abs().max()) <= 1e-12 * scale, k
+
+
 def test_fused_backward_is_reproducible_and_ragged_sizes():
     net = make_network(3, 6, 25, torch.nn.ReLU(), torch.float64, PolynomialBC())
     for n in (1, 7, 8, 9, 1000, 4099):
