@@ -69,7 +69,7 @@ int segment_reduce(int64_t n_out, const int32_t* seg, const int32_t* perm, const
 // pack_kernel behind a device-side dependency: wait until `progress` (bumped with release semantics by
 // the assembly kernel's warps) has reached `target`; the comparison is wrap-safe.
 template <typename T>
-__global__ void __launch_bounds__(256) pack_after_kernel(int n, const int32_t* __restrict__ idx, const T* src,
+__global__ void __launch_bounds__(128) pack_after_kernel(int n, const int32_t* __restrict__ idx, const T* src,
                                                          T* __restrict__ buf, const uint32_t* progress, uint32_t target) {
   if (threadIdx.x == 0) {
     uint32_t seen;
@@ -92,9 +92,11 @@ int iface_pack_after(int64_t n, const int32_t* idx, const T* src, T* buf, const 
   if (n == 0) return TFEM_OK;
   if (!idx || !src || !buf || !progress) return TFEM_ERR_BAD_ARG;
   if (n > kMaxIndex) return TFEM_ERR_TOO_LARGE;
-  // at most 16 small blocks: they spin beside a persistent grid and must fit in the slots it leaves free
-  const unsigned blocks = blocks_for(n, 256) < 16u ? blocks_for(n, 256) : 16u;
-  pack_after_kernel<T><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, idx, src, buf, progress, target);
+  // at most 32 small blocks of 128 threads: they spin beside a persistent grid and must fit in what it leaves free --
+  // next to a CTA of the role-specialised kernel (832 threads x 72 registers) an SM still has 5 632 registers, i.e. one
+  // such block (128 x 24) fits on EVERY SM, reserved or not
+  const unsigned blocks = blocks_for(n, 128) < 32u ? blocks_for(n, 128) : 32u;
+  pack_after_kernel<T><<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>((int)n, idx, src, buf, progress, target);
   return check_launch();
 }
 
@@ -114,7 +116,7 @@ int iface_unpack_add(int64_t n, const int32_t* idx, const T* buf, T* dst, void* 
   if (n == 0) return TFEM_OK;
   if (!idx || !buf || !dst) return TFEM_ERR_BAD_ARG;
   if (n > kMaxIndex) return TFEM_ERR_TOO_LARGE;
-  unpack_add_kernel<T><<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((int)n, idx, buf, dst);
+  unpack_add_kernel<T><<<blocks_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>((int)n, idx, buf, dst);
   return check_launch();
 }
 
