@@ -1,4 +1,4 @@
-"""P1 triangle: quadrature orders 1-4 (1/3/4/6 points), reference torch_fem/element/element_tri.py."""
+"""Triangle element: P1 / P2 shape functions, quadrature orders 1-4 (1/3/4/6 points), reference torch_fem/element/element_tri.py."""
 
 from __future__ import annotations
 
@@ -45,11 +45,20 @@ class ElementTri(AbstractElement):
         return torch.stack([1.0 - xi - eta, xi, eta], dim=-2)
 
     def compute_shape_functions(self, bar_coords: torch.Tensor, inv_map_jacobian: torch.Tensor):
-        if self.polynomial_order != 1:
-            # the reference carries P2 formulas (element_tri.py:43-70) but no basis can use
-            # them (basis/basis.py:50-51 rejects order 2); only P1 is part of the hot path
-            raise NotImplementedError("Polynomial order not implemented")
-        return bar_coords, self.barycentric_grad.to(inv_map_jacobian) @ inv_map_jacobian
+        grads = self.barycentric_grad.to(inv_map_jacobian)  # (3,2): gradients of the barycentric coordinates
+        if self.polynomial_order == 1:
+            return bar_coords, grads @ inv_map_jacobian
+        if self.polynomial_order == 2:
+            # Lagrange P2 (reference element_tri.py:43-70): vertex functions l (2 l - 1), edge functions 4 l_a l_b on the
+            # edges (1,2), (2,3), (3,1).  Host-side torch like the reference: no basis of either package assembles with
+            # them (basis/basis.py:50-51 rejects order 2), only P1 is on the kernel path.
+            lam = [bar_coords[..., k : k + 1, :] for k in range(3)]
+            pairs = ((0, 1), (1, 2), (2, 0))
+            values = [l * (2.0 * l - 1.0) for l in lam] + [4.0 * lam[a] * lam[b] for a, b in pairs]
+            slopes = [(4.0 * lam[k] - 1.0) * grads[k : k + 1] for k in range(3)]
+            slopes += [4.0 * (lam[b] * grads[a : a + 1] + lam[a] * grads[b : b + 1]) for a, b in pairs]
+            return torch.cat(values, dim=-2), torch.cat(slopes, dim=-2) @ inv_map_jacobian
+        raise NotImplementedError("Polynomial order not implemented")
 
     def compute_det_and_inv_map(self, map_jacobian: torch.Tensor):
         a, b = map_jacobian[..., 0:1, 0:1], map_jacobian[..., 0:1, 1:2]

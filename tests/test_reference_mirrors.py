@@ -170,3 +170,34 @@ def _check_refinement(Patches, centers, radius, math):
         assert torch.allclose(corner.abs().min(dim=-1).values, torch.zeros(4, 4, dtype=corner.dtype), atol=1e-15)  # corners on the axes
     c, r, v = patches.uniform_refine(1)
     assert c.shape[0] == 16 * 5 and torch.allclose(r[:64], torch.full((64, 1), 0.0625, dtype=r.dtype))
+
+
+def test_p2_shape_functions_match_the_reference():
+    """`ElementTri(2, k).compute_shape_functions` against outputs of the unmodified reference (element_tri.py:43-70;
+    tests/golden/p2_shape.npz made by tests/golden/make_golden_p2.py); order 3 elements still raise."""
+    import os
+
+    import numpy as np
+    import pytest
+    import torch
+
+    import pytorch_fem_solver_b200 as tfem
+
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "p2_shape.npz"))
+    previous = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        for order in (2, 3, 4):
+            element = tfem.ElementTri(2, order)
+            bar = element.compute_barycentric_coordinates(element.gaussian_nodes)
+            assert np.array_equal(bar.numpy(), golden[f"o{order}_bar"])
+            v, v_grad = element.compute_shape_functions(bar, torch.from_numpy(golden[f"o{order}_inv"]))
+            assert v.shape == golden[f"o{order}_v"].shape and v_grad.shape == golden[f"o{order}_v_grad"].shape
+            assert np.abs(v.numpy() - golden[f"o{order}_v"]).max() <= 1e-15
+            assert np.abs(v_grad.numpy() - golden[f"o{order}_v_grad"]).max() <= 1e-14
+            assert abs(float(v.sum(-2).max()) - 1.0) < 1e-14  # partition of unity
+        cubic = tfem.ElementTri(3, 2)
+        with pytest.raises(NotImplementedError):
+            cubic.compute_shape_functions(bar, torch.eye(2).reshape(1, 1, 2, 2))
+    finally:
+        torch.set_default_dtype(previous)
