@@ -35,16 +35,23 @@ class FeedForwardNeuralNetwork(torch.nn.Module):
     ):
         super().__init__()
         self._boundary_condition_modifier = boundary_condition_modifier or IdentityBC()
-        widths = [input_dimension] + [neurons_per_layers] * (nb_hidden_layers + 1)
+        self._neural_network = self.build_network(input_dimension, output_dimension, nb_hidden_layers, neurons_per_layers,
+                                                  activation_function, use_xavier_initialization)
+
+    def build_network(self, input_dimension: int, output_dimension: int, nb_layers: int, neurons_per_layers: int,
+                      activation_function: torch.nn.Module, use_xavier_initialization: bool) -> torch.nn.Sequential:
+        """Linear(in, w) act, `nb_layers` x (Linear(w, w) act), Linear(w, out) (reference :50-75)."""
+        widths = [input_dimension] + [neurons_per_layers] * (nb_layers + 1)
         layers: list[torch.nn.Module] = []
         for fan_in, fan_out in zip(widths[:-1], widths[1:]):
             layers += [torch.nn.Linear(fan_in, fan_out), activation_function]
         layers.append(torch.nn.Linear(neurons_per_layers, output_dimension))
-        self._neural_network = torch.nn.Sequential(*layers)
+        network = torch.nn.Sequential(*layers)
         if use_xavier_initialization:
-            for layer in self._neural_network:
+            for layer in network:
                 if isinstance(layer, torch.nn.Linear):
                     torch.nn.init.xavier_uniform_(layer.weight)
+        return network
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._neural_network(x) * self._boundary_condition_modifier(x)
