@@ -37,6 +37,15 @@ def reference_rows(coords, conn):
     return rows * n + col, matrix.values().numpy(), load.numpy().reshape(-1), np.diff(crow)
 
 
+
+def _say(message: str) -> None:
+    """One write per report line: `print` issues the text and the newline separately, and under torchrun the ranks'
+    lines then run into each other."""
+    import sys
+
+    sys.stdout.write(message + "\n")
+    sys.stdout.flush()
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--mode", default="weak", choices=["weak", "strong", "delaunay"])
@@ -147,7 +156,7 @@ def main():
     count[asm.plan.local_to_global[asm.plan.owned_rows]] = 1
     dist.all_reduce(count)
     assert int(count.sum()) == n_global and int(count.max()) == 1, "every global row must be owned exactly once"
-    print(f"rank {rank}/{world} [{args.mode} {nx}x{ny}]: {int(owned.sum())} owned rows, {int(mine.sum())} entries match the CPU "
+    _say(f"rank {rank}/{world} [{args.mode} {nx}x{ny}]: {int(owned.sum())} owned rows, {int(mine.sum())} entries match the CPU "
           f"restatement (matrix {err_m:.2e}, load {err_l:.2e}); {asm.full_plan.n_tiles} tiles, {asm.full_plan.n_templates} templates, "
           f"{asm.n_interface_tiles} interface tiles, {asm.exchange.bytes_sent // 2} interface bytes per assembly; {graph_note}", flush=True)
     dist.barrier()

@@ -22,6 +22,15 @@ from pytorch_fem_solver_b200 import distributed, forms, meshgen  # noqa: E402
 from tests.api_checks import rhs3  # noqa: E402
 
 
+
+def _say(message: str) -> None:
+    """One write per report line: `print` issues the text and the newline separately, and under torchrun the ranks'
+    lines then run into each other."""
+    import sys
+
+    sys.stdout.write(message + "\n")
+    sys.stdout.flush()
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nx", type=int, default=64)
@@ -63,7 +72,7 @@ def main():
     count[l2g[owned]] = 1
     dist.all_reduce(count)
     assert int(count.sum()) == pat.n_dof and int(count.max()) == 1, "every global row must be owned exactly once"
-    print(f"rank {rank}/{world} [7 fractures {args.nx}x{args.ny}, elements {asm.lo}:{asm.hi} of {basis._layout.n_total}]: "
+    _say(f"rank {rank}/{world} [7 fractures {args.nx}x{args.ny}, elements {asm.lo}:{asm.hi} of {basis._layout.n_total}]: "
           f"{int(owned.sum())} owned rows, {int(mine.sum())} entries match the whole-network assembly (matrix {err_m:.2e}, load {err_l:.2e}); "
           f"{asm.tile_plan.n_tiles} tiles, metric rows of {asm.metric_unit} elements, {asm.exchange.bytes_sent // 2} interface bytes per assembly",
           flush=True)

@@ -22,7 +22,11 @@ def _run(mode, nx, ny, rows_per_tile, port):
            "--master-port", str(port), os.path.join(REPO, "tests", "mgpu_check.py"), "--mode", mode, "--nx", str(nx), "--ny", str(ny),
            "--rows-per-tile", str(rows_per_tile)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=REPO)
-    report = [line for line in out.stdout.splitlines() if line.startswith("rank ")]
+    import re
+
+    # (one entry per rank even if two ranks' lines ran into each other on the shared pipe)
+    report = [piece for piece in re.split(r"(?=rank \d+/\d+ \[)", out.stdout) if piece.startswith("rank ")]
+    report = [piece.strip() for piece in report]
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     with open(os.path.join(REPO, "gpurun_out", f"mgpu_check_{mode}_{nx}x{ny}_n{n}.txt"), "w") as fh:
         fh.write("\n".join(report) + "\n")
