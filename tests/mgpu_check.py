@@ -38,7 +38,7 @@ def reference_rows(coords, conn):
 
 
 
-def _say(message: str) -> None:
+def _say(message: str, flush: bool = True) -> None:
     """One write per report line: `print` issues the text and the newline separately, and under torchrun the ranks'
     lines then run into each other."""
     import sys

@@ -23,7 +23,7 @@ from tests.api_checks import rhs3  # noqa: E402
 
 
 
-def _say(message: str) -> None:
+def _say(message: str, flush: bool = True) -> None:
     """One write per report line: `print` issues the text and the newline separately, and under torchrun the ranks'
     lines then run into each other."""
     import sys
