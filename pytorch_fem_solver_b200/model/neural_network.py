@@ -115,7 +115,10 @@ class FeedForwardNeuralNetwork(torch.nn.Module):
         return body * modifier, body_grad * modifier + body * modifier_grad.detach()
 
     def gradient(self, inputs: torch.Tensor) -> torch.Tensor:
-        """d u / d x at `inputs`, differentiable w.r.t. the parameters (reference :85-100)."""
+        """d u / d x at `inputs`, differentiable w.r.t. the parameters (reference :85-100).
+
+        On the fused path the result is NOT a function of `inputs` in the autograd graph (the points are quadrature
+        points): differentiate it once more w.r.t. the points through `laplacian`, or set `gradient_path = "torch"`."""
         inputs.requires_grad_(True)
         if self._fused_spec(inputs) is not None:
             return self.value_and_gradient(inputs)[1]
