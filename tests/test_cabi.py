@@ -36,6 +36,37 @@ def test_argument_validation_happens_before_any_launch():
     assert lib.tfem_quad_reduce_f64(3, 0, 9, None, 0, 0, None, None, None) == -1
 
 
+def test_argument_validation_of_the_round_two_entry_points():
+    """Symbolic phase, edge topology, MLP producer, tiled residual: bad arguments come back as status codes from the
+    host side (no launch, no GPU needed)."""
+    import ctypes
+
+    lib = _lib.load()
+    need = ctypes.c_int64(-1)
+    assert lib.tfem_csr_symbolic_workspace(-1, 10, ctypes.byref(need)) == -1
+    assert lib.tfem_csr_symbolic_workspace(10, 10, None) == -1
+    assert lib.tfem_csr_symbolic_workspace(2**28, 10, ctypes.byref(need)) == -4  # 9 n_el exceeds the 32-bit index range
+    assert lib.tfem_csr_symbolic(0, None, 10, None, 0, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.tfem_csr_symbolic(4, None, 10, None, 0, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.tfem_half_edges_workspace(-1, 1, ctypes.byref(need)) == -1
+    assert lib.tfem_half_edges(1, 4, 9, None, None, None, 0, None, None, None, None, None, None) == -1
+    assert lib.tfem_edge_cells(1, 4, 9, None, 3, None, None, 12, None, None, None) == -1  # n_sides is 1 or 2
+    assert lib.tfem_edge_cells(1, 0, 9, None, 2, None, None, 12, None, None, None) == 0  # no edges: nothing to do
+    assert lib.tfem_interior_edge_geometry_f64(1, 4, 9, 8, None, None, None, None, None, None, None, None) == -1
+    assert lib.tfem_interior_edge_geometry_f32(1, 0, 9, 8, None, None, None, None, None, None, None, None) == 0
+    assert lib.tfem_mlp_value_grad_f64(0, 2, 8, 1, 0, None, None, None, None, None) == 0
+    assert lib.tfem_mlp_value_grad_f64(5, 2, 8, 1, 0, None, None, None, None, None) == -1
+    assert lib.tfem_mlp_value_grad_f32(-1, 2, 8, 1, 0, None, None, None, None, None) == -1
+    assert lib.tfem_mlp_value_grad_bwd_f64(5, 2, 8, 1, 0, None, None, None, None, None, 4, None, None) == -1
+    fake = ctypes.addressof(ctypes.create_string_buffer(64))  # never dereferenced: the checks below fail first
+    assert lib.tfem_mlp_value_grad_f64(5, 2, 40, 1, 0, fake, fake, fake, fake, None) == -2  # wider than one lane per neuron
+    assert lib.tfem_mlp_value_grad_f64(5, 2, 8, 1, 7, fake, fake, fake, fake, None) == -2  # unknown activation
+    assert lib.tfem_mlp_value_grad_f64(5, 4, 8, 1, 0, fake, fake, fake, fake, None) == -1  # d is 1..3
+    assert lib.tfem_mlp_value_grad_bwd_f64(5, 2, 8, 9, 0, fake, fake, fake, fake, fake, 4, fake, None) == -2  # more than 7 square layers
+    assert lib.tfem_weak_residual_tiled_f64(None, None, 3, None, None, 0, None, None, None, None) == -1
+    assert lib.tfem_tri_p1_assemble_csr_ex_f64(None, None, 3, None, None, None, 0, None, None, None, None) == -1
+
+
 def test_product_has_no_cpu_path():
     """Without CUDA the basis constructor must fail loudly, not fall back."""
     import pytest
